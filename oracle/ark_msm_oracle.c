@@ -1,0 +1,517 @@
+/*
+ * ark_msm_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is a plain-C restatement of the arkworks (ark-ec / ark-ff 0.3.0) CPU path that the
+ * ZPrize-2022 prize-1a harness uses as its correctness reference:
+ *     VariableBaseMSM::multi_scalar_mul(bases, bigints)  ->  G1Projective
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * it.  The product (2022-entries_b200/) never links, imports or calls anything in oracle/.
+ *
+ * The arithmetic lives in crates.io dependencies that are NOT vendored in /root/reference at the
+ * pinned release (ark-ec 0.3.0, ark-ff 0.3.0, ark-bls12-377 0.3.0; pins: P1A/storswiftlabs/Cargo.lock).
+ * The restatement follows the in-tree copies of that code (paths relative to /root/reference,
+ * P1A = open-division/prize1-msm/prize1a-msm-gpu, P1B = open-division/prize1-msm/prize1b-msm-fpga):
+ *   - MSM:      P1A/speakspeak/src/util.rs:51-174 (near-verbatim ark-ec 0.3.0 multi_scalar_mul; the
+ *               original window rule is the commented block l.63-67), and
+ *               open-division/prize4-msm-wasm/snarkify/zprize-prize4-15ac8c55-arkworks-algebra/ec/src/msm/mod.rs:54-57
+ *               (ln_without_floats) + .../variable_base/mod.rs:68-160.
+ *   - Curve:    P1B/nickray/driver/algebra/ec/src/models/short_weierstrass_jacobian.rs
+ *               (add_assign_mixed madd-2007-bl l.662-729, double_in_place dbl-2009-l l.573-646,
+ *                add_assign add-2007-bl l.508-571, PartialEq l.330, compressed flags l.806-836).
+ *   - Field:    P1B/nickray/driver/algebra/ff/src/fields/models/fp/montgomery_backend.rs:89 (6xu64 CIOS);
+ *               moduli P1B/nickray/driver/bls12-377/src/fields/fq.rs:4, fr.rs:24;
+ *               constants cross-checked with P1A/6block/sppark/ff/bls12-377.hpp:10-39, bls12-381.hpp:10-37.
+ *   - Vectors:  open-division/prize7-msm-mobile/gnark/msm/bls12-377/marshal_zprize.go:24-150 (file format).
+ *
+ * Parity pin: the five arkworks-generated known-answer instances in tests/golden/ark377_*.bin
+ * (copied by tests/golden/make_golden.py) are reproduced byte-exactly by this file
+ * (tests/test_oracle_golden.py).  BLS12-381 has no vector in the reference: for that curve parity is
+ * "unpinned" by reference data and rests on oracle/ref_bigint.py (independent big-int) agreement.
+ *
+ * Build: make -C oracle   ->  oracle/liboracle.so   (gcc -O3 -pthread; no -march=native: the .so travels to the GPU box)
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <pthread.h>
+
+typedef unsigned __int128 u128;
+typedef struct { uint64_t l[6]; } fp_t;
+
+typedef struct {
+    fp_t p;            /* base-field modulus */
+    uint64_t pinv;     /* -p^-1 mod 2^64 */
+    fp_t R, R2;        /* 2^384 mod p, 2^768 mod p */
+    fp_t b;            /* curve coefficient b (Montgomery form), a = 0 */
+    uint64_t r[4];     /* scalar-field modulus */
+    int rbits;         /* MODULUS_BITS of the scalar field (253 / 255) */
+    fp_t gx, gy;       /* generator (Montgomery form) */
+    int ready;
+} curve_t;
+
+/* affine point in arkworks memory layout: x, y (6xu64 Montgomery), infinity flag, 7 pad = 104 B
+ * (short_weierstrass_jacobian.rs:50-57; P1B/hardcaml/.../rust_types.h:73-77) */
+typedef struct { fp_t x, y; uint8_t inf; uint8_t pad[7]; } aff_t;
+/* Jacobian x/z^2, y/z^3: 144 B (short_weierstrass_jacobian.rs:314-321) */
+typedef struct { fp_t x, y, z; } jac_t;
+
+/* ------------------------------------------------------------------------------------------- */
+/* multi-precision helpers                                                                       */
+static int mp_cmp(const uint64_t *a, const uint64_t *b, int n) {
+    for (int i = n - 1; i >= 0; i--) { if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1; }
+    return 0;
+}
+static uint64_t mp_add(uint64_t *r, const uint64_t *a, const uint64_t *b, int n) {
+    u128 c = 0; for (int i = 0; i < n; i++) { c += (u128)a[i] + b[i]; r[i] = (uint64_t)c; c >>= 64; } return (uint64_t)c;
+}
+static uint64_t mp_sub(uint64_t *r, const uint64_t *a, const uint64_t *b, int n) {
+    uint64_t br = 0;
+    for (int i = 0; i < n; i++) { u128 t = (u128)a[i] - b[i] - br; r[i] = (uint64_t)t; br = (uint64_t)(t >> 64) & 1; }
+    return br;
+}
+static int mp_is_zero(const uint64_t *a, int n) { uint64_t o = 0; for (int i = 0; i < n; i++) o |= a[i]; return o == 0; }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Fp: 6x64 Montgomery (montgomery_backend.rs:89, CIOS)                                          */
+static void fp_add(const curve_t *C, fp_t *r, const fp_t *a, const fp_t *b) {
+    fp_t t; mp_add(t.l, a->l, b->l, 6);              /* p < 2^383: no carry out */
+    if (mp_cmp(t.l, C->p.l, 6) >= 0) mp_sub(t.l, t.l, C->p.l, 6);
+    *r = t;
+}
+static void fp_sub(const curve_t *C, fp_t *r, const fp_t *a, const fp_t *b) {
+    fp_t t; if (mp_sub(t.l, a->l, b->l, 6)) mp_add(t.l, t.l, C->p.l, 6);
+    *r = t;
+}
+static void fp_dbl(const curve_t *C, fp_t *r, const fp_t *a) { fp_add(C, r, a, a); }
+static void fp_neg(const curve_t *C, fp_t *r, const fp_t *a) {
+    if (mp_is_zero(a->l, 6)) { *r = *a; return; }
+    mp_sub(r->l, C->p.l, a->l, 6);
+}
+static void fp_mul(const curve_t *C, fp_t *r, const fp_t *a, const fp_t *b) {
+    uint64_t t[8] = {0};
+    for (int i = 0; i < 6; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 6; j++) { c += (u128)a->l[j] * b->l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[6] = (uint64_t)c; t[7] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * C->pinv;
+        c = (u128)m * C->p.l[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 6; j++) { c += (u128)m * C->p.l[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[5] = (uint64_t)c; t[6] = t[7] + (uint64_t)(c >> 64);
+    }
+    fp_t o; memcpy(o.l, t, 48);
+    if (t[6] || mp_cmp(o.l, C->p.l, 6) >= 0) mp_sub(o.l, o.l, C->p.l, 6);
+    *r = o;
+}
+static void fp_sqr(const curve_t *C, fp_t *r, const fp_t *a) { fp_mul(C, r, a, a); }
+static int fp_is_zero(const fp_t *a) { return mp_is_zero(a->l, 6); }
+static int fp_eq(const fp_t *a, const fp_t *b) { return memcmp(a, b, 48) == 0; }
+static void fp_from_canon(const curve_t *C, fp_t *r, const fp_t *a) { fp_mul(C, r, a, &C->R2); }
+static void fp_to_canon(const curve_t *C, fp_t *r, const fp_t *a) { fp_t one = {{1, 0, 0, 0, 0, 0}}; fp_mul(C, r, a, &one); }
+/* r = a^e, e little-endian limbs */
+static void fp_pow(const curve_t *C, fp_t *r, const fp_t *a, const uint64_t *e, int n) {
+    fp_t acc = C->R, base = *a;
+    for (int i = 0; i < n * 64; i++) {
+        if ((e[i / 64] >> (i % 64)) & 1) fp_mul(C, &acc, &acc, &base);
+        fp_sqr(C, &base, &base);
+    }
+    *r = acc;
+}
+static void fp_inv(const curve_t *C, fp_t *r, const fp_t *a) {
+    fp_t e = C->p; uint64_t two[6] = {2, 0, 0, 0, 0, 0}; mp_sub(e.l, e.l, two, 6);
+    fp_pow(C, r, a, e.l, 6);
+}
+/* Tonelli-Shanks; returns 0 if a is a non-residue.  The 2-Sylow generator z^q is cached per curve. */
+static int fp_sqrt(const curve_t *C, fp_t *r, const fp_t *a) {
+    if (fp_is_zero(a)) { *r = *a; return 1; }
+    static fp_t c0[2]; static int s0[2]; static uint64_t q0[2][6], q1h[2][6]; static int have[2];
+    int id = (C->rbits == 253) ? 0 : 1;
+    if (!have[id]) {
+        uint64_t q[6]; memcpy(q, C->p.l, 48); q[0] -= 1; int s = 0;                    /* p - 1 = q * 2^s */
+        while (!(q[0] & 1)) { for (int i = 0; i < 6; i++) q[i] = (q[i] >> 1) | (i < 5 ? q[i + 1] << 63 : 0); s++; }
+        uint64_t eh[6]; memcpy(eh, C->p.l, 48); eh[0] -= 1;                             /* (p-1)/2 */
+        for (int i = 0; i < 6; i++) eh[i] = (eh[i] >> 1) | (i < 5 ? eh[i + 1] << 63 : 0);
+        fp_t z = C->R, chk;
+        for (;;) { fp_add(C, &z, &z, &C->R); fp_pow(C, &chk, &z, eh, 6); if (!fp_eq(&chk, &C->R)) break; }
+        fp_pow(C, &c0[id], &z, q, 6);
+        uint64_t o1[6] = {1, 0, 0, 0, 0, 0}, t[6]; mp_add(t, q, o1, 6);
+        for (int i = 0; i < 6; i++) t[i] = (t[i] >> 1) | (i < 5 ? t[i + 1] << 63 : 0);  /* (q+1)/2 */
+        memcpy(q0[id], q, 48); memcpy(q1h[id], t, 48); s0[id] = s; have[id] = 1;
+    }
+    fp_t c = c0[id], x, t, a2;
+    fp_pow(C, &x, a, q1h[id], 6);                      /* a^((q+1)/2) */
+    fp_sqr(C, &t, &x); fp_inv(C, &a2, a); fp_mul(C, &t, &t, &a2);   /* t = a^q */
+    int m = s0[id];
+    while (!fp_eq(&t, &C->R)) {
+        int i = 0; fp_t tt = t;
+        while (!fp_eq(&tt, &C->R)) { fp_sqr(C, &tt, &tt); i++; if (i >= m) return 0; }
+        fp_t bb = c; for (int k = 0; k < m - i - 1; k++) fp_sqr(C, &bb, &bb);
+        fp_mul(C, &x, &x, &bb); fp_sqr(C, &c, &bb); fp_mul(C, &t, &t, &c); m = i;
+    }
+    fp_t chk2; fp_sqr(C, &chk2, &x); if (!fp_eq(&chk2, a)) return 0;
+    *r = x; return 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* curve constants                                                                               */
+static curve_t g_curves[2];
+
+static void curve_setup(curve_t *C, const uint64_t p[6], const uint64_t r[4], int rbits, uint64_t b,
+                        const uint64_t gx[6], const uint64_t gy[6]) {
+    memcpy(C->p.l, p, 48); memcpy(C->r, r, 32); C->rbits = rbits;
+    uint64_t inv = 1; for (int i = 0; i < 6; i++) inv *= 2 - p[0] * inv;   /* Newton: p^-1 mod 2^64 */
+    C->pinv = (uint64_t)0 - inv;
+    /* R = 2^384 mod p, R2 = 2^768 mod p by repeated doubling of 1 */
+    fp_t t = {{1, 0, 0, 0, 0, 0}};
+    for (int i = 0; i < 768; i++) {
+        fp_add(C, &t, &t, &t);
+        if (i == 383) C->R = t;
+    }
+    C->R2 = t;
+    fp_t bc = {{b, 0, 0, 0, 0, 0}}; fp_from_canon(C, &C->b, &bc);
+    fp_t g; memcpy(g.l, gx, 48); fp_from_canon(C, &C->gx, &g);
+    memcpy(g.l, gy, 48); fp_from_canon(C, &C->gy, &g);
+    C->ready = 1;
+}
+
+/* curve ids: 0 = BLS12-377, 1 = BLS12-381 */
+static const curve_t *get_curve(int id) {
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_mutex_lock(&mu);
+    if (!g_curves[0].ready) {
+        /* P1B/nickray/driver/bls12-377/src/fields/fq.rs:4, fr.rs:24; g1.rs:159-165 */
+        static const uint64_t p377[6] = {0x8508c00000000001ULL, 0x170b5d4430000000ULL, 0x1ef3622fba094800ULL,
+                                         0x1a22d9f300f5138fULL, 0xc63b05c06ca1493bULL, 0x01ae3a4617c510eaULL};
+        static const uint64_t r377[4] = {0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL,
+                                         0x12ab655e9a2ca556ULL};
+        static const uint64_t gx377[6] = {0xeab9b16eb21be9efULL, 0xd5481512ffcd394eULL, 0x188282c8bd37cb5cULL,
+                                          0x85951e2caa9d41bbULL, 0xc8fc6225bf87ff54ULL, 0x008848defe740a67ULL};
+        static const uint64_t gy377[6] = {0xfd82de55559c8ea6ULL, 0xc2fe3d3634a9591aULL, 0x6d182ad44fb82305ULL,
+                                          0xbd7fb348ca3e52d9ULL, 0x1f674f5d30afeec4ULL, 0x01914a69c5102eFFULL};
+        curve_setup(&g_curves[0], p377, r377, 253, 1, gx377, gy377);
+        /* P1A/6block/sppark/ff/bls12-381.hpp:10-37; generator = the standard BLS12-381 G1 generator */
+        static const uint64_t p381[6] = {0xb9feffffffffaaabULL, 0x1eabfffeb153ffffULL, 0x6730d2a0f6b0f624ULL,
+                                         0x64774b84f38512bfULL, 0x4b1ba7b6434bacd7ULL, 0x1a0111ea397fe69aULL};
+        static const uint64_t r381[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL,
+                                         0x73eda753299d7d48ULL};
+        static const uint64_t gx381[6] = {0xfb3af00adb22c6bbULL, 0x6c55e83ff97a1aefULL, 0xa14e3a3f171bac58ULL,
+                                          0xc3688c4f9774b905ULL, 0x2695638c4fa9ac0fULL, 0x17f1d3a73197d794ULL};
+        static const uint64_t gy381[6] = {0x0caa232946c5e7e1ULL, 0xd03cc744a2888ae4ULL, 0x00db18cb2c04b3edULL,
+                                          0xfcf5e095d5d00af6ULL, 0xa09e30ed741d8ae4ULL, 0x08b3f481e3aaa0f1ULL};
+        curve_setup(&g_curves[1], p381, r381, 255, 4, gx381, gy381);
+    }
+    pthread_mutex_unlock(&mu);
+    return (id == 0 || id == 1) ? &g_curves[id] : NULL;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Jacobian group ops, as in short_weierstrass_jacobian.rs                                       */
+static int jac_is_zero(const jac_t *a) { return fp_is_zero(&a->z); }
+static void jac_set_zero(const curve_t *C, jac_t *a) { a->x = C->R; a->y = C->R; memset(&a->z, 0, 48); } /* (1,1,0) l.417-423 */
+
+/* dbl-2009-l, a = 0 (l.573-610) */
+static void jac_double(const curve_t *C, jac_t *s) {
+    if (jac_is_zero(s)) return;
+    fp_t a, b, c, d, e, f, t;
+    fp_sqr(C, &a, &s->x); fp_sqr(C, &b, &s->y); fp_sqr(C, &c, &b);
+    fp_add(C, &t, &s->x, &b); fp_sqr(C, &t, &t); fp_sub(C, &t, &t, &a); fp_sub(C, &t, &t, &c); fp_dbl(C, &d, &t);
+    fp_dbl(C, &e, &a); fp_add(C, &e, &e, &a);
+    fp_sqr(C, &f, &e);
+    fp_mul(C, &s->z, &s->z, &s->y); fp_dbl(C, &s->z, &s->z);
+    fp_sub(C, &t, &f, &d); fp_sub(C, &s->x, &t, &d);
+    fp_dbl(C, &c, &c); fp_dbl(C, &c, &c); fp_dbl(C, &c, &c);
+    fp_sub(C, &t, &d, &s->x); fp_mul(C, &t, &t, &e); fp_sub(C, &s->y, &t, &c);
+}
+
+/* madd-2007-bl (l.662-729) */
+static void jac_add_mixed(const curve_t *C, jac_t *s, const aff_t *o) {
+    if (o->inf) return;
+    if (jac_is_zero(s)) { s->x = o->x; s->y = o->y; s->z = C->R; return; }
+    fp_t z1z1, u2, s2, h, hh, i, j, r, v, t;
+    fp_sqr(C, &z1z1, &s->z);
+    fp_mul(C, &u2, &o->x, &z1z1);
+    fp_mul(C, &s2, &o->y, &s->z); fp_mul(C, &s2, &s2, &z1z1);
+    if (fp_eq(&s->x, &u2) && fp_eq(&s->y, &s2)) { jac_double(C, s); return; }
+    fp_sub(C, &h, &u2, &s->x);
+    fp_sqr(C, &hh, &h);
+    fp_dbl(C, &i, &hh); fp_dbl(C, &i, &i);
+    fp_mul(C, &j, &h, &i);
+    fp_sub(C, &r, &s2, &s->y); fp_dbl(C, &r, &r);
+    fp_mul(C, &v, &s->x, &i);
+    fp_sqr(C, &t, &r); fp_sub(C, &t, &t, &j); fp_sub(C, &t, &t, &v); fp_sub(C, &t, &t, &v);
+    fp_mul(C, &j, &j, &s->y); fp_dbl(C, &j, &j);
+    s->x = t;
+    fp_sub(C, &t, &v, &s->x); fp_mul(C, &t, &t, &r); fp_sub(C, &s->y, &t, &j);
+    fp_add(C, &t, &s->z, &h); fp_sqr(C, &t, &t); fp_sub(C, &t, &t, &z1z1); fp_sub(C, &s->z, &t, &hh);
+}
+
+/* add-2007-bl (l.508-571) */
+static void jac_add(const curve_t *C, jac_t *s, const jac_t *o) {
+    if (jac_is_zero(s)) { *s = *o; return; }
+    if (jac_is_zero(o)) return;
+    fp_t z1z1, z2z2, u1, u2, s1, s2, h, i, j, r, v, t;
+    fp_sqr(C, &z1z1, &s->z); fp_sqr(C, &z2z2, &o->z);
+    fp_mul(C, &u1, &s->x, &z2z2); fp_mul(C, &u2, &o->x, &z1z1);
+    fp_mul(C, &s1, &s->y, &o->z); fp_mul(C, &s1, &s1, &z2z2);
+    fp_mul(C, &s2, &o->y, &s->z); fp_mul(C, &s2, &s2, &z1z1);
+    if (fp_eq(&u1, &u2) && fp_eq(&s1, &s2)) { jac_double(C, s); return; }
+    fp_sub(C, &h, &u2, &u1);
+    fp_dbl(C, &i, &h); fp_sqr(C, &i, &i);
+    fp_mul(C, &j, &h, &i);
+    fp_sub(C, &r, &s2, &s1); fp_dbl(C, &r, &r);
+    fp_mul(C, &v, &u1, &i);
+    fp_sqr(C, &t, &r); fp_sub(C, &t, &t, &j); fp_sub(C, &t, &t, &v); fp_sub(C, &s->x, &t, &v);
+    fp_sub(C, &t, &v, &s->x); fp_mul(C, &t, &t, &r);
+    fp_mul(C, &s1, &s1, &j); fp_dbl(C, &s1, &s1);
+    fp_sub(C, &s->y, &t, &s1);
+    fp_add(C, &t, &s->z, &o->z); fp_sqr(C, &t, &t); fp_sub(C, &t, &t, &z1z1); fp_sub(C, &t, &t, &z2z2);
+    fp_mul(C, &s->z, &t, &h);
+}
+
+/* into_affine: (x/z^2, y/z^3); zero -> (0, 1, inf) (l.154-156) */
+static void jac_to_affine(const curve_t *C, aff_t *a, const jac_t *s) {
+    memset(a, 0, sizeof(*a));
+    if (jac_is_zero(s)) { a->y = C->R; a->inf = 1; return; }
+    fp_t zi, zi2, zi3; fp_inv(C, &zi, &s->z); fp_sqr(C, &zi2, &zi); fp_mul(C, &zi3, &zi2, &zi);
+    fp_mul(C, &a->x, &s->x, &zi2); fp_mul(C, &a->y, &s->y, &zi3);
+}
+
+static int aff_on_curve(const curve_t *C, const aff_t *a) {
+    if (a->inf) return 1;
+    fp_t l, r; fp_sqr(C, &l, &a->y); fp_sqr(C, &r, &a->x); fp_mul(C, &r, &r, &a->x); fp_add(C, &r, &r, &C->b);
+    return fp_eq(&l, &r);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* scalar helpers (BigInteger256)                                                                */
+static inline uint64_t scalar_bits(const uint64_t s[4], int start, int c) {   /* divn(start) then % 2^c */
+    if (start >= 256) return 0;
+    int w = start / 64, b = start % 64;
+    uint64_t v = s[w] >> b;
+    if (b && w + 1 < 4) v |= s[w + 1] << (64 - b);
+    return c >= 64 ? v : (v & (((uint64_t)1 << c) - 1));
+}
+
+/* ark_std::log2 = ceil(log2 x); ln_without_floats(a) = log2(a) * 69 / 100  (msm/mod.rs:54-57) */
+static int ark_log2(uint64_t x) {
+    if (x == 0) return 0;
+    if ((x & (x - 1)) == 0) return 63 - __builtin_clzll(x);
+    return 64 - __builtin_clzll(x);
+}
+int oracle_ark_window_bits(uint64_t size) { return size < 32 ? 3 : (ark_log2(size) * 69 / 100) + 2; }
+
+typedef struct {
+    const curve_t *C; const aff_t *bases; const uint64_t *scalars; size_t n; int c; int nwin;
+    jac_t *window_sums; int next; pthread_mutex_t mu;
+} msm_job_t;
+
+/* one window, exactly as the closure in multi_scalar_mul (util.rs:80-140) */
+static void msm_window(const msm_job_t *J, int w, jac_t *out) {
+    const curve_t *C = J->C; int c = J->c; int w_start = w * c;
+    size_t nb = ((size_t)1 << c) - 1;
+    jac_t res; jac_set_zero(C, &res);
+    jac_t *buckets = (jac_t *)malloc(nb * sizeof(jac_t));
+    for (size_t k = 0; k < nb; k++) jac_set_zero(C, &buckets[k]);
+    for (size_t i = 0; i < J->n; i++) {
+        const uint64_t *s = J->scalars + 4 * i;
+        if (mp_is_zero(s, 4)) continue;                               /* filter(|(s,_)| !s.is_zero()) */
+        if (s[0] == 1 && !s[1] && !s[2] && !s[3]) {                   /* scalar == fr_one */
+            if (w_start == 0) jac_add_mixed(C, &res, &J->bases[i]);
+        } else {
+            uint64_t d = scalar_bits(s, w_start, c);
+            if (d != 0) jac_add_mixed(C, &buckets[d - 1], &J->bases[i]);
+        }
+    }
+    jac_t running; jac_set_zero(C, &running);
+    for (size_t k = nb; k-- > 0;) { jac_add(C, &running, &buckets[k]); jac_add(C, &res, &running); }
+    free(buckets);
+    *out = res;
+}
+static void *msm_worker(void *arg) {
+    msm_job_t *J = (msm_job_t *)arg;
+    for (;;) {
+        pthread_mutex_lock(&J->mu); int w = J->next++; pthread_mutex_unlock(&J->mu);
+        if (w >= J->nwin) break;
+        msm_window(J, w, &J->window_sums[w]);
+    }
+    return NULL;
+}
+
+/* VariableBaseMSM::multi_scalar_mul.  bases: n x 104 B, scalars: n x 32 B, out: 144 B Jacobian.
+ * c_override = 0 -> arkworks window rule.  nthreads = rayon pool size stand-in (one task per window). */
+int oracle_ark_msm(int curve, const void *bases, const void *scalars, size_t n, void *out, int nthreads, int c_override) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    msm_job_t J; J.C = C; J.bases = (const aff_t *)bases; J.scalars = (const uint64_t *)scalars; J.n = n;
+    J.c = c_override > 0 ? c_override : oracle_ark_window_bits(n);
+    J.nwin = (C->rbits + J.c - 1) / J.c;                               /* (0..num_bits).step_by(c) */
+    J.window_sums = (jac_t *)malloc(J.nwin * sizeof(jac_t)); J.next = 0; pthread_mutex_init(&J.mu, NULL);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > J.nwin) nthreads = J.nwin;
+    pthread_t th[256]; if (nthreads > 256) nthreads = 256;
+    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, msm_worker, &J);
+    msm_worker(&J);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    /* lowest + fold(rev(window_sums[1..]), |total, s| { total += s; c doublings }) (util.rs:143-167) */
+    jac_t total; jac_set_zero(C, &total);
+    for (int w = J.nwin - 1; w >= 1; w--) { jac_add(C, &total, &J.window_sums[w]); for (int k = 0; k < J.c; k++) jac_double(C, &total); }
+    jac_t res = J.window_sums[0]; jac_add(C, &res, &total);
+    memcpy(out, &res, sizeof(res));
+    free(J.window_sums); pthread_mutex_destroy(&J.mu);
+    return 0;
+}
+
+/* sum_i s_i * P_i by plain double-and-add (test-templates/src/msm.rs:7-38 naive_var_base_msm) */
+int oracle_naive_msm(int curve, const void *bases, const void *scalars, size_t n, void *out) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    const aff_t *B = (const aff_t *)bases; const uint64_t *S = (const uint64_t *)scalars;
+    jac_t acc; jac_set_zero(C, &acc);
+    for (size_t i = 0; i < n; i++) {
+        jac_t t; jac_set_zero(C, &t);
+        for (int b = 255; b >= 0; b--) { jac_double(C, &t); if ((S[4 * i + b / 64] >> (b % 64)) & 1) jac_add_mixed(C, &t, &B[i]); }
+        jac_add(C, &acc, &t);
+    }
+    memcpy(out, &acc, sizeof(acc));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* conversions used by the tests                                                                 */
+int oracle_jac_to_affine(int curve, const void *jac, size_t n, void *aff) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    for (size_t i = 0; i < n; i++) jac_to_affine(C, (aff_t *)aff + i, (const jac_t *)jac + i);
+    return 0;
+}
+/* XYZZ (x = X/ZZ, y = Y/ZZZ; 4 x 48 B Montgomery; ZZ = 0 -> infinity) -> canonical affine */
+int oracle_xyzz_to_affine(int curve, const void *xyzz, size_t n, void *aff) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    const fp_t *q = (const fp_t *)xyzz; aff_t *o = (aff_t *)aff;
+    for (size_t i = 0; i < n; i++, q += 4) {
+        memset(&o[i], 0, sizeof(aff_t));
+        if (fp_is_zero(&q[2])) { o[i].y = C->R; o[i].inf = 1; continue; }
+        fp_t zi, zzi; fp_inv(C, &zzi, &q[2]); fp_inv(C, &zi, &q[3]);
+        fp_mul(C, &o[i].x, &q[0], &zzi); fp_mul(C, &o[i].y, &q[1], &zi);
+    }
+    return 0;
+}
+int oracle_jac_eq(int curve, const void *a, const void *b) {           /* PartialEq l.330 */
+    const curve_t *C = get_curve(curve); const jac_t *p = a, *q = b;
+    if (jac_is_zero(p)) return jac_is_zero(q);
+    if (jac_is_zero(q)) return 0;
+    fp_t z1, z2, l, r; fp_sqr(C, &z1, &p->z); fp_sqr(C, &z2, &q->z);
+    fp_mul(C, &l, &p->x, &z2); fp_mul(C, &r, &q->x, &z1); if (!fp_eq(&l, &r)) return 0;
+    fp_mul(C, &z1, &z1, &p->z); fp_mul(C, &z2, &z2, &q->z);
+    fp_mul(C, &l, &p->y, &z2); fp_mul(C, &r, &q->y, &z1); return fp_eq(&l, &r);
+}
+int oracle_on_curve(int curve, const void *aff, size_t n) {
+    const curve_t *C = get_curve(curve);
+    for (size_t i = 0; i < n; i++) if (!aff_on_curve(C, (const aff_t *)aff + i)) return 0;
+    return 1;
+}
+/* Jacobian add / mixed add / double on arrays, for the device EC parity tests */
+int oracle_jac_add_mixed_n(int curve, void *acc, const void *aff, size_t n) {
+    const curve_t *C = get_curve(curve); for (size_t i = 0; i < n; i++) jac_add_mixed(C, (jac_t *)acc + i, (const aff_t *)aff + i); return 0;
+}
+int oracle_jac_add_n(int curve, void *acc, const void *o, size_t n) {
+    const curve_t *C = get_curve(curve); for (size_t i = 0; i < n; i++) jac_add(C, (jac_t *)acc + i, (const jac_t *)o + i); return 0;
+}
+int oracle_jac_double_n(int curve, void *acc, size_t n) {
+    const curve_t *C = get_curve(curve); for (size_t i = 0; i < n; i++) jac_double(C, (jac_t *)acc + i); return 0;
+}
+int oracle_aff_neg_n(int curve, void *aff, size_t n) {
+    const curve_t *C = get_curve(curve); for (size_t i = 0; i < n; i++) { aff_t *a = (aff_t *)aff + i; if (!a->inf) fp_neg(C, &a->y, &a->y); } return 0;
+}
+/* field ops on arrays (Montgomery form in and out): op 0 mul, 1 add, 2 sub, 3 sqr, 4 inv */
+int oracle_fp_op(int curve, int op, const void *a, const void *b, void *r, size_t n) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    const fp_t *A = a, *B = b; fp_t *O = r;
+    for (size_t i = 0; i < n; i++) {
+        switch (op) {
+        case 0: fp_mul(C, &O[i], &A[i], &B[i]); break;
+        case 1: fp_add(C, &O[i], &A[i], &B[i]); break;
+        case 2: fp_sub(C, &O[i], &A[i], &B[i]); break;
+        case 3: fp_sqr(C, &O[i], &A[i]); break;
+        case 4: fp_inv(C, &O[i], &A[i]); break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+int oracle_fp_convert(int curve, int to_mont, const void *a, void *r, size_t n) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    for (size_t i = 0; i < n; i++) { if (to_mont) fp_from_canon(C, (fp_t *)r + i, (const fp_t *)a + i); else fp_to_canon(C, (fp_t *)r + i, (const fp_t *)a + i); }
+    return 0;
+}
+/* constants out: p(48) R(48) R2(48) pinv(8) r(32) gx(48) gy(48) b(48) */
+int oracle_constants(int curve, void *out) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    uint8_t *o = out;
+    memcpy(o, &C->p, 48); memcpy(o + 48, &C->R, 48); memcpy(o + 96, &C->R2, 48); memcpy(o + 144, &C->pinv, 8);
+    memcpy(o + 152, C->r, 32); memcpy(o + 184, &C->gx, 48); memcpy(o + 232, &C->gy, 48); memcpy(o + 280, &C->b, 48);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* ark-serialize 0.3 compressed G1Affine (48 B): x canonical LE; byte 47 bit 6 = infinity,        */
+/* bit 7 = "y is the larger of {y, p-y}" (serialize/src/flags.rs:64-131; sw_jacobian.rs:806-818)  */
+static int y_is_larger(const curve_t *C, const fp_t *y_mont) {
+    fp_t y, ny; fp_to_canon(C, &y, y_mont); fp_t n; fp_neg(C, &n, y_mont); fp_to_canon(C, &ny, &n);
+    return mp_cmp(y.l, ny.l, 6) > 0;
+}
+int oracle_decompress(int curve, const void *in, size_t n, void *aff_out) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    const uint8_t *p = in; aff_t *o = aff_out;
+    for (size_t i = 0; i < n; i++, p += 48) {
+        memset(&o[i], 0, sizeof(aff_t));
+        uint8_t flags = p[47] & 0xC0;
+        if (flags & 0x40) { o[i].y = C->R; o[i].inf = 1; continue; }
+        fp_t x; memcpy(x.l, p, 48); x.l[5] &= 0x3FFFFFFFFFFFFFFFULL;
+        if (mp_cmp(x.l, C->p.l, 6) >= 0) return -2;
+        fp_t xm, rhs, y; fp_from_canon(C, &xm, &x);
+        fp_sqr(C, &rhs, &xm); fp_mul(C, &rhs, &rhs, &xm); fp_add(C, &rhs, &rhs, &C->b);
+        if (!fp_sqrt(C, &y, &rhs)) return -3;
+        int want_larger = (flags & 0x80) != 0;
+        if (y_is_larger(C, &y) != want_larger) fp_neg(C, &y, &y);
+        o[i].x = xm; o[i].y = y;
+    }
+    return 0;
+}
+int oracle_compress(int curve, const void *aff_in, size_t n, void *out) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    const aff_t *a = aff_in; uint8_t *p = out;
+    for (size_t i = 0; i < n; i++, p += 48) {
+        memset(p, 0, 48);
+        if (a[i].inf) { p[47] = 0x40; continue; }
+        fp_t x; fp_to_canon(C, &x, &a[i].x); memcpy(p, x.l, 48);
+        if (y_is_larger(C, &a[i].y)) p[47] |= 0x80;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* deterministic test inputs (tests only; the product has its own generator)                      */
+static uint64_t splitmix64(uint64_t *s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
+}
+/* n distinct-looking points k_i * G (k_i 64-bit from SplitMix64(seed)), canonical affine */
+int oracle_gen_points(int curve, uint64_t seed, size_t n, void *aff_out) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    aff_t g; memset(&g, 0, sizeof(g)); g.x = C->gx; g.y = C->gy;
+    aff_t *o = aff_out;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t k = splitmix64(&seed) | 1;
+        jac_t t; jac_set_zero(C, &t);
+        for (int b = 63; b >= 0; b--) { jac_double(C, &t); if ((k >> b) & 1) jac_add_mixed(C, &t, &g); }
+        jac_to_affine(C, &o[i], &t);
+    }
+    return 0;
+}
+/* n scalars uniform in [0, r) by rejection on the top limb mask */
+int oracle_gen_scalars(int curve, uint64_t seed, size_t n, void *out) {
+    const curve_t *C = get_curve(curve); if (!C) return -1;
+    uint64_t *s = out; uint64_t mask = C->rbits % 64 ? (((uint64_t)1 << (C->rbits % 64)) - 1) : ~(uint64_t)0;
+    for (size_t i = 0; i < n; i++) {
+        do { for (int k = 0; k < 4; k++) s[4 * i + k] = splitmix64(&seed); s[4 * i + 3] &= mask; } while (mp_cmp(&s[4 * i], C->r, 4) >= 0);
+    }
+    return 0;
+}

@@ -1,0 +1,45 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.build()
+    return O
+
+
+@pytest.fixture(scope="session")
+def golden_instances(oracle):
+    """The five arkworks-generated instances: list of dict(aff=np.uint8[n,104], scalars=np.uint8[n,32], result=bytes)."""
+    cache = os.path.join("/tmp", "b200msm_golden_cache.npz")
+    inst = oracle.read_golden(os.path.join(GOLDEN, "ark377_points.bin"), os.path.join(GOLDEN, "ark377_scalars.bin"),
+                              os.path.join(GOLDEN, "ark377_result.bin"))
+    affs = None
+    if os.path.exists(cache):
+        try:
+            z = np.load(cache)
+            affs = [z[f"a{k}"] for k in range(len(inst))]
+            if any(len(a) != len(inst[k][1]) for k, a in enumerate(affs)):
+                affs = None
+        except Exception:
+            affs = None
+    if affs is None:
+        affs = [oracle.decompress(P) for P, _, _ in inst]
+        try:
+            np.savez(cache, **{f"a{k}": a for k, a in enumerate(affs)})
+        except Exception:
+            pass
+    return [dict(aff=affs[k], scalars=inst[k][1], result=inst[k][2]) for k in range(len(inst))]

@@ -1,0 +1,114 @@
+"""Pins the CPU oracle against the reference's own known-answer vectors.
+
+The vectors were produced by arkworks VariableBaseMSM::multi_scalar_mul
+(open-division/prize7-msm-mobile/gnark/src/lib.rs:245-283) and are checked by the reference in
+gnark/msm/bls12-377/zprize_test.go:15-40.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import ref_bigint as RB
+
+SIZES = [16384, 16384, 256, 16, 65536]
+
+
+def test_manifest_hashes():
+    man = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))
+    for name, meta in man.items():
+        data = open(os.path.join(GOLDEN, name), "rb").read()
+        assert len(data) == meta["bytes"] and hashlib.sha256(data).hexdigest() == meta["sha256"], name
+
+
+def test_constants_match_reference_tables(oracle):
+    # three in-tree copies (sppark bls12-377.hpp:10-39, ff_config.cuh:13-40, SHM.cu:13-48)
+    c = oracle.constants(0)
+    assert c["p"] == RB.CURVES[0]["p"] and c["r"] == RB.CURVES[0]["r"]
+    assert c["R"] == 0x008d6661e2fdf49a4cf495bf803c84e87b4e97b76e7c63059f7db3a98a7d3ff251409f837fffffb102cdffffffffff68
+    assert c["R2"] == 0x006dfccb1e914b88837e92f041790bf9bfdf7d03827dc3ac22a5f11162d6b46d0329fcaab00431b1b786686c9400cd22
+    assert c["pinv"] == 0x8508bfffffffffff
+    c1 = oracle.constants(1)
+    assert c1["p"] == RB.CURVES[1]["p"] and c1["r"] == RB.CURVES[1]["r"] and c1["pinv"] == 0x89f3fffcfffcfffd
+    for cid in (0, 1):
+        cc, p = oracle.constants(cid), RB.CURVES[cid]["p"]
+        assert cc["R"] == (1 << 384) % p and cc["R2"] == (1 << 768) % p
+        assert cc["gx"] == RB.CURVES[cid]["gx"] * (1 << 384) % p and cc["b"] == RB.CURVES[cid]["b"] * (1 << 384) % p
+
+
+def test_ark_window_rule(oracle):
+    # N = 2^16 -> 13, 2^20 -> 15, 2^24 -> 18, 2^26 -> 19, 2^28 -> 21; < 32 -> 3
+    assert [oracle.window_bits(1 << k) for k in (16, 20, 24, 26, 28)] == [13, 15, 18, 19, 21]
+    assert oracle.window_bits(16) == 3 and oracle.window_bits(31) == 3 and oracle.window_bits(33) == 6
+
+
+@pytest.mark.parametrize("k", range(5))
+def test_c_oracle_reproduces_arkworks_results(oracle, golden_instances, k):
+    g = golden_instances[k]
+    assert len(g["scalars"]) == SIZES[k]
+    assert oracle.on_curve(g["aff"])
+    jac = oracle.ark_msm(g["aff"], g["scalars"])
+    assert oracle.compress(oracle.jac_to_affine(jac)).tobytes() == g["result"]
+    if k == 3:
+        assert g["result"].hex() == ("e84820ff9ba244d9f3a700a1daf0117b5550fa15c6c75ddc8ad535bc55a2db57"
+                                     "056489f85e22762e61f4f6bbd7660680")
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_python_bigint_reproduces_arkworks_results(k):
+    inst = list(RB.read_instances(os.path.join(GOLDEN, "ark377_points.bin"), os.path.join(GOLDEN, "ark377_scalars.bin")))
+    res = open(os.path.join(GOLDEN, "ark377_result.bin"), "rb").read()
+    P, S = inst[k]
+    pts = [RB.decompress(b) for b in P]
+    assert RB.compress(RB.naive_msm(pts, S)) == res[48 * k: 48 * k + 48]
+
+
+def test_all_infinity_instance(oracle):
+    # yyteam/mobileMSM/app/src/main/assets/zero-points-test: 256 bases, every one flagged infinity
+    inst = oracle.read_golden(os.path.join(GOLDEN, "ark377_allinf_points.bin"), os.path.join(GOLDEN, "ark377_allinf_scalars.bin"))
+    P, S, _ = inst[0]
+    aff = oracle.decompress(P)
+    assert aff[:, 96].all()
+    out = oracle.jac_to_affine(oracle.ark_msm(aff, S))
+    assert out[0, 96] == 1
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_c_oracle_vs_python_bigint_random(oracle, curve):
+    """Independent implementations agree on fresh inputs (the only pin BLS12-381 has)."""
+    n = 24
+    aff = oracle.gen_points(n, seed=11 + curve, curve=curve)
+    sc = oracle.gen_scalars(n, seed=12 + curve, curve=curve)
+    sc[0, :] = 0
+    sc[1, :] = 0
+    sc[1, 0] = 1                                       # scalar == 1 shortcut
+    r = RB.CURVES[curve]["r"]
+    sc[2, :] = np.frombuffer((r - 1).to_bytes(32, "little"), np.uint8)
+    aff[3, :] = 0
+    aff[3, 96] = 1                                     # infinity base
+    aff[5] = aff[4]                                    # equal bases
+    aff[7] = oracle.aff_neg(aff[6:7], curve)[0]
+    sc[7] = sc[6]                                      # P and -P with equal scalars cancel
+    assert oracle.on_curve(aff, curve)
+    pts = [RB.from_mont_affine_bytes(bytes(a), curve) for a in aff]
+    S = [int.from_bytes(bytes(s), "little") for s in sc]
+    want = RB.to_mont_affine_bytes(RB.naive_msm(pts, S, curve), curve)
+    for c in (0, 5):
+        got = oracle.jac_to_affine(oracle.ark_msm(aff, sc, curve, c=c), curve)[0]
+        assert bytes(got[:97]) == want[:97]
+    got = oracle.jac_to_affine(oracle.naive_msm(aff, sc, curve), curve)[0]
+    assert bytes(got[:97]) == want[:97]
+
+
+def test_pippenger_vs_naive_4096(oracle):
+    n = 4096
+    aff = oracle.gen_points(64, seed=5)
+    aff = np.tile(aff, (n // 64, 1))                   # harness-style replication (P1A/yrrid/src/util.rs:26-28)
+    sc = oracle.gen_scalars(n, seed=6)
+    a = oracle.jac_to_affine(oracle.ark_msm(aff, sc))
+    b = oracle.jac_to_affine(oracle.naive_msm(aff, sc))
+    assert a.tobytes() == b.tobytes()
+    assert oracle.jac_eq(oracle.ark_msm(aff, sc), oracle.naive_msm(aff, sc))
