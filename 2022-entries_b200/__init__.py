@@ -1,0 +1,295 @@
+"""b200msm -- host side of the B200 MSM engine (mirror of the ZPrize prize-1a Rust shim).
+
+The reference harness is Rust (`multi_scalar_mult_init` / `multi_scalar_mult`,
+P1A/storswiftlabs/src/lib.rs:43-98, P1A/yrrid/src/lib.rs:38-90; P1A = open-division/prize1-msm/prize1a-msm-gpu);
+this image has no Rust toolchain, so the same two calls are mirrored here over the same `extern "C"` symbols
+(include/b200msm.h).  The Rust binding a maintainer would add is in INTEGRATION.md and rust/.
+
+Everything here is plumbing over `libb200msm.so` (hand-written sm_100a CUDA).  There is no CPU path: if the
+library is missing or no CUDA device is usable, calls raise.
+
+Layouts (arkworks in-memory): G1Affine 104 B (x, y 6xu64 Montgomery + infinity byte at 96), scalar 32 B
+(4xu64 integer in [0, r)), G1Projective 144 B (Jacobian x, y, z).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200msm.so")
+BLS12_377, BLS12_381 = 0, 1
+BASES_HARNESS, BASES_DISTINCT = 0, 1
+AFFINE_BYTES, SCALAR_BYTES, PROJECTIVE_BYTES, XYZZ_BYTES = 104, 32, 144, 192
+
+_lib = None
+
+
+class MsmError(RuntimeError):
+    pass
+
+
+class _RustError(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int), ("message", ctypes.c_void_p)]
+
+
+class _FfiContext(ctypes.Structure):       # #[repr(C)] struct MultiScalarMultContext { context: *mut c_void }
+    _fields_ = [("context", ctypes.c_void_p)]
+
+
+def lib():
+    """Load libb200msm.so (built in-tree by __graft_entry__.build() / make -C csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MsmError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, i32, sz = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_size_t
+    L.b200msm_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32]
+    L.b200msm_destroy.argtypes = [vp]
+    L.b200msm_last_error.argtypes = [vp]
+    L.b200msm_last_error.restype = ctypes.c_char_p
+    L.b200msm_set_stream.argtypes = [vp, vp]
+    L.b200msm_set_bases.argtypes = [vp, vp, u64, u64]
+    L.b200msm_set_bases_generated.argtypes = [vp, u64, u64, i32, u64]
+    L.b200msm_get_bases.argtypes = [vp, vp, u64, u64]
+    L.b200msm_generate_scalars.argtypes = [vp, vp, u64, u64]
+    L.b200msm_msm_device.argtypes = [vp, vp, u64, vp]
+    L.b200msm_msm_host.argtypes = [vp, vp, u64, u64, vp]
+    L.b200msm_msm_partial_device.argtypes = [vp, vp, u64, vp]
+    L.b200msm_combine_device.argtypes = [vp, vp, i32, vp]
+    L.b200msm_sync.argtypes = [vp]
+    L.b200msm_get_info.argtypes = [vp, ctypes.POINTER(u64)]
+    L.b200msm_get_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.b200msm_test_fp_op.argtypes = [i32, i32, vp, vp, vp, u64]
+    L.b200msm_test_ec_op.argtypes = [i32, i32, vp, vp, u64, i32]
+    L.mult_pippenger_init.argtypes = [ctypes.POINTER(_FfiContext), vp, sz, sz]
+    L.mult_pippenger_init.restype = _RustError
+    L.mult_pippenger_inf.argtypes = [ctypes.POINTER(_FfiContext), vp, vp, sz, sz, vp, sz]
+    L.mult_pippenger_inf.restype = _RustError
+    L.mult_pippenger_free.argtypes = [ctypes.POINTER(_FfiContext)]
+    L.mult_pippenger_free.restype = _RustError
+    L.MSMAllocContext.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    L.MSMAllocContext.restype = vp
+    L.MSMFreeContext.argtypes = [vp]
+    L.MSMFreeContext.restype = ctypes.c_int32
+    L.MSMPreprocessPoints.argtypes = [vp, vp, ctypes.c_uint32]
+    L.MSMPreprocessPoints.restype = ctypes.c_int32
+    L.MSMRun.argtypes = [vp, vp, vp, ctypes.c_uint32]
+    L.MSMRun.restype = ctypes.c_int32
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bases",
+    "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
+    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
+    "b200msm_get_stage_ms", "b200msm_test_fp_op", "b200msm_test_ec_op", "mult_pippenger_init", "mult_pippenger_inf",
+    "mult_pippenger_free", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
+]
+
+
+def _as_u8(a, row_bytes, what):
+    a = np.ascontiguousarray(a)
+    flat = a.view(np.uint8).reshape(-1)
+    if flat.size % row_bytes:
+        raise ValueError(f"{what}: byte length {flat.size} is not a multiple of {row_bytes}")
+    return flat
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _take_rust_error(err, what):
+    if err.code != 0:
+        msg = ctypes.string_at(err.message).decode() if err.message else ""
+        if err.message:
+            ctypes.CDLL(None).free(ctypes.c_void_p(err.message))     # the Rust side owns and frees the message
+        raise MsmError(f"{what}: error {err.code}: {msg}")           # the Rust shim panics here
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The harness API (Family A symbols), same names and argument meaning as the Rust shim
+class MultiScalarMultContext:
+    def __init__(self):
+        self.ffi = _FfiContext(None)
+        self.npoints = 0
+
+    def free(self):
+        if self.ffi.context:
+            lib().mult_pippenger_free(ctypes.byref(self.ffi))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def multi_scalar_mult_init(points):
+    """points: n arkworks G1Affine records (uint8[n, 104]).  Uploads them and builds the base tables (untimed
+    in the harness)."""
+    pts = _as_u8(points, AFFINE_BYTES, "points")
+    ctx = MultiScalarMultContext()
+    ctx.npoints = pts.size // AFFINE_BYTES
+    err = lib().mult_pippenger_init(ctypes.byref(ctx.ffi), _ptr(pts), ctx.npoints, AFFINE_BYTES)
+    _take_rust_error(err, "mult_pippenger_init")
+    return ctx
+
+
+def multi_scalar_mult(context, points, scalars):
+    """scalars: batches * n 32-byte integers.  Returns uint8[batches, 144] Jacobian results."""
+    pts = _as_u8(points, AFFINE_BYTES, "points")
+    sc = _as_u8(scalars, SCALAR_BYTES, "scalars")
+    npoints = pts.size // AFFINE_BYTES
+    nscalars = sc.size // SCALAR_BYTES
+    if npoints == 0 or nscalars % npoints != 0:
+        raise MsmError("length mismatch")                            # the Rust shim panics with the same message
+    batches = nscalars // npoints
+    out = np.zeros((batches, PROJECTIVE_BYTES), np.uint8)
+    err = lib().mult_pippenger_inf(ctypes.byref(context.ffi), _ptr(out), _ptr(pts), npoints, batches, _ptr(sc), AFFINE_BYTES)
+    _take_rust_error(err, "mult_pippenger_inf")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Family B (yrrid): thin wrappers, same call order as P1A/yrrid/src/lib.rs:38-90
+class YrridContext:
+    def __init__(self, max_points=1 << 26, max_batches=16):
+        self.handle = lib().MSMAllocContext(max_points, max_batches)
+        if not self.handle:
+            raise MsmError("MSMAllocContext failed")
+
+    def preprocess_points(self, points):
+        pts = _as_u8(points, AFFINE_BYTES, "points")
+        self.npoints = pts.size // AFFINE_BYTES
+        rc = lib().MSMPreprocessPoints(self.handle, _ptr(pts), self.npoints)
+        if rc != 0:
+            raise MsmError(f"Error {rc} occurred in C code")
+
+    def run(self, scalars):
+        sc = _as_u8(scalars, SCALAR_BYTES, "scalars")
+        n = sc.size // SCALAR_BYTES
+        out = np.zeros((max(n // max(self.npoints, 1), 1), PROJECTIVE_BYTES), np.uint8)
+        rc = lib().MSMRun(self.handle, _ptr(out), _ptr(sc), n)
+        if rc != 0:
+            raise MsmError(f"Error {rc} occurred in C code")
+        return out
+
+    def free(self):
+        if self.handle:
+            lib().MSMFreeContext(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Native interface: device-resident scalars, generated bases, partial results for point sharding, stage timings
+class Engine:
+    STAGES = ("digits_hist", "scan_scatter", "pieces", "accumulate", "bucket_reduce", "finalize")
+
+    def __init__(self, curve=BLS12_377, device=0, window_bits=0, tables=0):
+        self.h = ctypes.c_void_p()
+        rc = lib().b200msm_create(ctypes.byref(self.h), curve, device, window_bits, tables)
+        if rc != 0:
+            raise MsmError(f"b200msm_create: {rc}: {lib().b200msm_last_error(None).decode()}")
+        self.curve, self.device = curve, device
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise MsmError(f"{what}: {rc}: {lib().b200msm_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            lib().b200msm_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._ck(lib().b200msm_set_stream(self.h, ctypes.c_void_p(cuda_stream)), "set_stream")
+
+    def set_bases(self, points, stride=AFFINE_BYTES):
+        pts = _as_u8(points, stride, "points")
+        self.n = pts.size // stride
+        self._ck(lib().b200msm_set_bases(self.h, _ptr(pts), self.n, stride), "set_bases")
+
+    def set_bases_generated(self, n, seed=1, mode=BASES_HARNESS, distinct=1 << 15):
+        self.n = n
+        self._ck(lib().b200msm_set_bases_generated(self.h, n, seed, mode, distinct), "set_bases_generated")
+
+    def get_bases(self, first, n):
+        out = np.zeros((n, 96), np.uint8)
+        self._ck(lib().b200msm_get_bases(self.h, _ptr(out), first, n), "get_bases")
+        return out
+
+    def generate_scalars(self, dev_ptr, n, seed):
+        self._ck(lib().b200msm_generate_scalars(self.h, ctypes.c_void_p(dev_ptr), n, seed), "generate_scalars")
+
+    def msm_device(self, scalars_dev_ptr, n, out_dev_ptr):
+        self._ck(lib().b200msm_msm_device(self.h, ctypes.c_void_p(scalars_dev_ptr), n, ctypes.c_void_p(out_dev_ptr)), "msm_device")
+
+    def msm_partial_device(self, scalars_dev_ptr, n, out_xyzz_dev_ptr):
+        self._ck(lib().b200msm_msm_partial_device(self.h, ctypes.c_void_p(scalars_dev_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_partial_device")
+
+    def combine_device(self, xyzz_dev_ptr, count, out_dev_ptr):
+        self._ck(lib().b200msm_combine_device(self.h, ctypes.c_void_p(xyzz_dev_ptr), count, ctypes.c_void_p(out_dev_ptr)), "combine_device")
+
+    def msm_host(self, scalars, batches=1):
+        """scalars: host buffer (numpy array or a raw address of pinned memory) of batches * n * 32 bytes."""
+        out = np.zeros((batches, PROJECTIVE_BYTES), np.uint8)
+        if isinstance(scalars, int):
+            p = ctypes.c_void_p(scalars)
+        else:
+            sc = _as_u8(scalars, SCALAR_BYTES, "scalars")
+            if sc.size != batches * self.n * SCALAR_BYTES:
+                raise MsmError("length mismatch")
+            p = _ptr(sc)
+        self._ck(lib().b200msm_msm_host(self.h, p, self.n, batches, _ptr(out)), "msm_host")
+        return out
+
+    def sync(self):
+        self._ck(lib().b200msm_sync(self.h), "sync")
+
+    def info(self):
+        a = (ctypes.c_uint64 * 8)()
+        lib().b200msm_get_info(self.h, a)
+        keys = ("n", "window_bits", "windows", "tables", "folded_windows", "buckets", "lmax", "launches")
+        return dict(zip(keys, [int(v) for v in a]))
+
+    def stage_ms(self):
+        a = (ctypes.c_float * 6)()
+        self._ck(lib().b200msm_get_stage_ms(self.h, a), "get_stage_ms")
+        return dict(zip(self.STAGES, [float(v) for v in a]))
+
+
+def test_fp_op(curve, op, a, b=None):
+    a = _as_u8(a, 48, "a")
+    b = a if b is None else _as_u8(b, 48, "b")
+    r = np.zeros_like(a)
+    rc = lib().b200msm_test_fp_op(curve, op, _ptr(a), _ptr(b), _ptr(r), a.size // 48)
+    if rc != 0:
+        raise MsmError(f"b200msm_test_fp_op: {rc}: {lib().b200msm_last_error(None).decode()}")
+    return r.reshape(-1, 48)
+
+
+def test_ec_op(curve, op, acc, other=None, reps=1):
+    acc = _as_u8(acc, XYZZ_BYTES, "acc").copy()
+    o = None if other is None else _as_u8(other, 96 if op != 1 else XYZZ_BYTES, "other")
+    rc = lib().b200msm_test_ec_op(curve, op, _ptr(acc), _ptr(o) if o is not None else None, acc.size // XYZZ_BYTES, reps)
+    if rc != 0:
+        raise MsmError(f"b200msm_test_ec_op: {rc}: {lib().b200msm_last_error(None).decode()}")
+    return acc.reshape(-1, XYZZ_BYTES)

@@ -15,6 +15,12 @@
 #pragma once
 #include "fp.cuh"
 
+#if defined(__CUDACC__)
+#define EC_NI __device__ __noinline__
+#else
+#define EC_NI inline
+#endif
+
 namespace b200msm {
 
 struct affine_t { fp x, y; };            // canonical (< p) Montgomery limbs; 96 bytes in the device tables
@@ -143,6 +149,33 @@ template <class C> struct Ec {
         F::mul(x, a.x, z2);
         F::mul(x, x, i2);
         F::mul(y, a.y, i);
+        F::reduce(x);
+        F::reduce(y);
+    }
+    // Non-inlined entry points for the cold kernels (bucket reduction, finalize, table build): one copy of each body
+    // per curve instead of one per call site.
+    EC_NI static void add_ni(xyzz_t &a, const xyzz_t &b) { add(a, b); }
+    EC_NI static void dbl_ni(xyzz_t &a) { dbl(a); }
+    EC_NI static void madd_ni(xyzz_t &acc, const fp &x2, const fp &y2) { madd(acc, x2, y2); }
+    EC_NI static void dbl_affine_ni(xyzz_t &r, const fp &x, const fp &y) { dbl_affine(r, x, y); }
+    EC_NI static void mul_ni(fp &r, const fp &a, const fp &b) { F::mul(r, a, b); }
+    EC_NI static void inv_ni(fp &r, const fp &a) {
+        fp acc;
+        F::set_one(acc);
+        for (int i = 383; i >= 0; i--) {
+            mul_ni(acc, acc, acc);
+            if ((F::pm2_limb(i >> 5) >> (i & 31)) & 1) mul_ni(acc, acc, a);
+        }
+        r = acc;
+    }
+    EC_NI static void to_affine_ni(fp &x, fp &y, const xyzz_t &a) {
+        fp i, i2, z2;
+        inv_ni(i, a.zzz);
+        mul_ni(i2, i, i);
+        mul_ni(z2, a.zz, a.zz);
+        mul_ni(x, a.x, z2);
+        mul_ni(x, x, i2);
+        mul_ni(y, a.y, i);
         F::reduce(x);
         F::reduce(y);
     }

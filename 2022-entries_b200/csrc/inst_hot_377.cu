@@ -1,0 +1,2 @@
+#include "launch_hot.inl"
+namespace b200msm { template struct LaunchHot<Bls12_377>; }

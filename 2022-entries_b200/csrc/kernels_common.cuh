@@ -1,0 +1,180 @@
+// kernels_common.cuh -- curve-independent kernels (included by msm.cu only):
+//   k_scan_*         a5  exclusive prefix sums (bucket offsets, piece offsets)
+//   k_piece_*        a5  split buckets into pieces of at most Lmax points, order pieces by decreasing length
+//   k_convert_points a11 arkworks G1Affine records -> base table 0 + infinity bitmask;  k_replicate: test bases
+#pragma once
+#include "kernels_util.cuh"
+
+namespace b200msm {
+
+// ---------------------------------------------------------------------------------------------
+// exclusive prefix sum of uint32 (three launches; blocks of 256 threads x 8 elements)
+#define SCAN_TPB 256
+#define SCAN_EPT 8
+template <int MODE>   // MODE 0: in = raw counts;  MODE 1: in = pieces per bucket = max(1, ceil(count / lmax))
+__device__ __forceinline__ uint32_t scan_input(uint32_t v, uint32_t lmax) {
+    if (MODE == 0) return v;
+    return v == 0 ? 1u : (v + lmax - 1) / lmax;
+}
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_block_sums(const uint32_t *__restrict__ in, uint32_t n, uint32_t lmax, uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t sh[SCAN_TPB / 32];
+    uint32_t base = blockIdx.x * (SCAN_TPB * SCAN_EPT) + threadIdx.x * SCAN_EPT;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_EPT; k++) if (base + k < n) sum += scan_input<MODE>(in[base + k], lmax);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < SCAN_TPB / 32; k++) t += sh[k];
+        block_sums[blockIdx.x] = t;
+    }
+}
+// single block: exclusive scan of block_sums in place; total written to block_sums[nblocks]
+__global__ void __launch_bounds__(1024) k_scan_top(uint32_t *block_sums, uint32_t nblocks) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblocks; base += 1024) {
+        uint32_t idx = base + threadIdx.x;
+        uint32_t v = idx < nblocks ? block_sums[idx] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t incl = sh[threadIdx.x];
+        uint32_t r0 = running;
+        if (idx < nblocks) block_sums[idx] = r0 + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = r0 + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nblocks] = running;
+}
+// out[i] = exclusive prefix;  out[n] = total;  optional second copy (the scatter cursors)
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_apply(const uint32_t *__restrict__ in, uint32_t n, uint32_t lmax, const uint32_t *__restrict__ block_sums,
+                                                        uint32_t *__restrict__ out, uint32_t *__restrict__ out2) {
+    __shared__ uint32_t sh[SCAN_TPB];
+    uint32_t base = blockIdx.x * (SCAN_TPB * SCAN_EPT) + threadIdx.x * SCAN_EPT;
+    uint32_t v[SCAN_EPT], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_EPT; k++) { v[k] = (base + k < n) ? scan_input<MODE>(in[base + k], lmax) : 0; sum += v[k]; }
+    sh[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < SCAN_TPB; o <<= 1) {
+        uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = block_sums[blockIdx.x] + sh[threadIdx.x] - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_EPT; k++) {
+        if (base + k < n) { out[base + k] = run; if (out2) out2[base + k] = run; }
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_TPB - 1) out[n] = block_sums[gridDim.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// a5: pieces.  Bucket k owns pieces [piece_off[k], piece_off[k+1]); piece s of bucket k covers
+// refs[bucket_off[k] + s*lmax ...] (at most lmax entries).  With uniform scalars every bucket is one piece; the
+// split only exists so that a skewed scalar set (all equal, sparse, ...) cannot serialise on one thread.
+// Pieces are then ordered by decreasing length (counting sort) so the 32 lanes of a warp run the same trip count.
+#define PIECE_TPB 256
+__global__ void __launch_bounds__(PIECE_TPB) k_piece_fill(const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ piece_off, uint32_t nbuckets,
+                                                          uint32_t lmax, uint32_t *__restrict__ piece_start, uint32_t *__restrict__ piece_len,
+                                                          uint32_t *__restrict__ len_hist) {
+    extern __shared__ uint32_t sh_hist[];   // lmax + 1 bins
+    for (uint32_t b = threadIdx.x; b <= lmax; b += blockDim.x) sh_hist[b] = 0;
+    __syncthreads();
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nbuckets) {
+        uint32_t start = bucket_off[k], cnt = bucket_off[k + 1] - start;
+        uint32_t j = piece_off[k], np = piece_off[k + 1] - j;
+        for (uint32_t s = 0; s < np; s++) {
+            uint32_t len = cnt > lmax ? lmax : cnt;
+            piece_start[j + s] = start;
+            piece_len[j + s] = len;
+            atomicAdd(&sh_hist[len], 1u);
+            start += len;
+            cnt -= len;
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= lmax; b += blockDim.x) if (sh_hist[b]) atomicAdd(&len_hist[b], sh_hist[b]);
+}
+// single block: cursor[len] = number of pieces strictly longer than len (descending order start positions)
+__global__ void __launch_bounds__(1024) k_piece_len_scan(const uint32_t *__restrict__ len_hist, uint32_t lmax, uint32_t *__restrict__ len_cursor) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    // walk lengths from lmax down to 0 in tiles of 1024
+    for (uint32_t base = 0; base <= lmax; base += 1024) {
+        uint32_t r = base + threadIdx.x;                  // rank in descending order
+        uint32_t v = r <= lmax ? len_hist[lmax - r] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t r0 = running, incl = sh[threadIdx.x];
+        if (r <= lmax) len_cursor[lmax - r] = r0 + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = r0 + incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(PIECE_TPB) k_piece_order(const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr, uint32_t lmax,
+                                                           uint32_t *__restrict__ len_cursor, uint32_t *__restrict__ order) {
+    extern __shared__ uint32_t sh[];        // [0, lmax]: local histogram, then reserved global base per length
+    for (uint32_t b = threadIdx.x; b <= lmax; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    uint32_t np = *npieces_ptr;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t len = 0, rank = 0;
+    if (j < np) { len = piece_len[j]; rank = atomicAdd(&sh[len], 1u); }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= lmax; b += blockDim.x) { uint32_t cnt = sh[b]; if (cnt) sh[b] = atomicAdd(&len_cursor[b], cnt); }
+    __syncthreads();
+    if (j < np) order[sh[len] + rank] = j;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11 (curve-independent part)
+// arkworks G1Affine (x, y: 6 x u64 Montgomery; infinity flag at byte 96; stride bytes) -> table 0 + infinity bitmask
+__global__ void __launch_bounds__(256) k_convert_points(const uint8_t *__restrict__ src, uint32_t n, uint32_t stride, affine_t *__restrict__ table0, uint32_t *__restrict__ infmask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool inf = false;
+    if (i < n) {
+        const uint64_t *p = reinterpret_cast<const uint64_t *>(src + (size_t)i * stride);   // 104 and 96 are both multiples of 8
+        uint64_t *d = reinterpret_cast<uint64_t *>(table0 + i);
+#pragma unroll
+        for (int k = 0; k < 12; k++) d[k] = p[k];
+        inf = stride > 96 && src[(size_t)i * stride + 96] != 0;
+    }
+    uint32_t bits = __ballot_sync(0xffffffffu, inf);
+    if ((threadIdx.x & 31) == 0 && i < n) infmask[i >> 5] = bits;
+}
+// replicate the first `have` entries of a table up to n (vector doubling, as the reference generator does)
+__global__ void __launch_bounds__(256) k_replicate(affine_t *table, uint32_t have, uint32_t n) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one uint4 per thread
+    size_t total = (size_t)(n - have) * 6;
+    if (idx >= total) return;
+    size_t e = have + idx / 6, k = idx % 6;
+    reinterpret_cast<uint4 *>(table + e)[k] = reinterpret_cast<const uint4 *>(table + (e % have))[k];
+}
+
+}  // namespace b200msm

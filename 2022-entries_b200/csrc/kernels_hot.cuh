@@ -1,0 +1,135 @@
+// kernels_hot.cuh -- the per-MSM kernels that touch every scalar / every point (templated on the curve):
+//   k_digits<PASS>   a4  signed-digit window decomposition fused with the bucket histogram (PASS 0) and with the
+//                        scatter of point references into per-bucket lists (PASS 1)
+//   k_accumulate     a6  the hot loop: thread = piece of a bucket, XYZZ += affine, points prefetched with cp.async
+// (a4 / a6 = rows of SURVEY.md section 8a; reference counterparts are listed in DESIGN.md.)
+#pragma once
+#include "kernels_util.cuh"
+#include "launch.h"
+
+namespace b200msm {
+
+// ---------------------------------------------------------------------------------------------
+// a4: scalar -> signed window digits.
+//
+//   s <- s mod r;  if the top scalar bit is set, s <- r - s and every digit's sign flips ((r-s)(-P) = sP), so
+//   s < 2^(SCALAR_BITS-1) and W = ceil(SCALAR_BITS / c) windows absorb the last carry.
+//   digit d_w in [-2^(c-1), 2^(c-1)]:  raw + carry > 2^(c-1)  ->  d = raw + carry - 2^c, carry 1.
+//   window w is served from base table j = w / F (holding 2^(c*F*j) P) into folded window f = w % F:
+//   bucket key = f * 2^(c-1) + |d| - 1,  point reference = j*N + i, bit 31 = negate.
+// PASS 0 counts keys; PASS 1 takes a slot in the bucket's list (cursor pre-loaded with the bucket offsets).
+template <class C> struct ScalarOps {
+    // s >= k*r ?  s -= k*r   (k*r must fit 256 bits)
+    template <int K> __device__ static void csub_kr(uint32_t (&s)[8]) {
+        uint32_t kr[8];
+        uint64_t carry = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)C::r(i) * K + carry; kr[i] = (uint32_t)t; carry = t >> 32; }
+        uint32_t t[8];
+        t[0] = sub_cc(s[0], kr[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) t[i] = subc_cc(s[i], kr[i]);
+        uint32_t borrow = subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = borrow ? s[i] : t[i];
+    }
+    __device__ static void mod_r(uint32_t (&s)[8]) {
+        if (C::SCALAR_BITS <= 253) { csub_kr<8>(s); csub_kr<4>(s); }
+        csub_kr<2>(s);
+        csub_kr<1>(s);
+    }
+    // returns true when s was replaced by r - s
+    __device__ static bool fold_top_bit(uint32_t (&s)[8]) {
+        const int tb = C::SCALAR_BITS - 1;
+        if (!((s[tb >> 5] >> (tb & 31)) & 1)) return false;
+        s[0] = sub_cc(C::r(0), s[0]);
+#pragma unroll
+        for (int i = 1; i < 8; i++) s[i] = subc_cc(C::r(i), s[i]);
+        return true;
+    }
+};
+
+template <class C, int PASS>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
+                                                uint32_t n, uint32_t table_stride, int c, int W, int F,
+                                                uint32_t *__restrict__ counters, uint32_t *__restrict__ refs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (infmask[i >> 5] & (1u << (i & 31))) return;       // base at infinity contributes nothing
+    uint32_t s[9];
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
+        uint4 lo = __ldg(p), hi = __ldg(p + 1);
+        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+    }
+    uint32_t(&s8)[8] = reinterpret_cast<uint32_t(&)[8]>(s);
+    ScalarOps<C>::mod_r(s8);
+    bool neg = ScalarOps<C>::fold_top_bit(s8);
+    s[8] = 0;
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        int pos = w * c;
+        int wi = pos >> 5, sh = pos & 31;
+        uint64_t v = (uint64_t)s[wi] | ((uint64_t)s[wi + 1 > 8 ? 8 : wi + 1] << 32);
+        uint32_t d = ((uint32_t)(v >> sh) & mask) + carry;
+        bool flip = d > half;
+        if (flip) d = (1u << c) - d;
+        carry = flip ? 1u : 0u;
+        if (d == 0) continue;
+        uint32_t key = (uint32_t)(w % F) * half + d - 1;
+        if (PASS == 0) {
+            atomicAdd(&counters[key], 1u);
+        } else {
+            uint32_t slot = atomicAdd(&counters[key], 1u);
+            refs[slot] = ((uint32_t)(w / F) * table_stride + i) | ((neg != flip) ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6: bucket accumulation.  One thread sums one piece: acc (XYZZ, registers) += table[ref] for each reference in
+// the piece.  The next point's 96 bytes are fetched with six 16-byte cp.async into the thread's own shared-memory
+// slots ([stage][16-byte chunk][thread]: conflict-free) while the current mixed add (~3000 integer instructions)
+// runs, so the random gather latency is hidden by one stage of prefetch.  Results go to res[piece].
+template <class C>
+__global__ void __launch_bounds__(ACC_TPB) k_accumulate(const affine_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+                                                        const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
+                                                        const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
+                                                        xyzz_t *__restrict__ res) {
+    __shared__ uint4 stage[2][6][ACC_TPB];
+    uint32_t j = blockIdx.x * ACC_TPB + threadIdx.x;
+    if (j >= *npieces_ptr) return;
+    const uint32_t piece = order[j];
+    const uint32_t start = piece_start[piece], len = piece_len[piece];
+    xyzz_t acc;
+    Ec<C>::set_inf(acc);
+    uint32_t ref = 0, ref_next = 0;
+    if (len) {
+        ref = __ldg(refs + start);
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref & 0x7fffffffu));
+#pragma unroll
+        for (int k = 0; k < 6; k++) cp_async16(&stage[0][k][threadIdx.x], src + k);
+    }
+    cp_async_commit();
+    for (uint32_t i = 0; i < len; i++) {
+        if (i + 1 < len) {
+            ref_next = __ldg(refs + start + i + 1);
+            const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref_next & 0x7fffffffu));
+#pragma unroll
+            for (int k = 0; k < 6; k++) cp_async16(&stage[(i + 1) & 1][k][threadIdx.x], src + k);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        affine_t pt;
+        uint4 *t = reinterpret_cast<uint4 *>(&pt);
+#pragma unroll
+        for (int k = 0; k < 6; k++) t[k] = stage[i & 1][k][threadIdx.x];
+        if (ref >> 31) Fp<C>::template neg<1>(pt.y, pt.y);
+        Ec<C>::madd(acc, pt.x, pt.y);
+        ref = ref_next;
+    }
+    store_xyzz(res + piece, acc);
+}
+
+}  // namespace b200msm

@@ -1,0 +1,35 @@
+// launch.h -- host-callable launchers of the curve-templated kernels.  Each curve's hot and cold kernels live in
+// their own translation unit (inst_*.cu) so the library builds in parallel; msm.cu only sees these declarations.
+#pragma once
+#include <cuda_runtime.h>
+#include "ec.cuh"
+
+namespace b200msm {
+
+#define FIN_MAX_TERMS 24
+struct fin_term_t { const xyzz_t *arr; uint32_t n; uint32_t stride_f; uint32_t shift; uint32_t kind; };
+struct fin_args_t { fin_term_t term[FIN_MAX_TERMS]; int nterms; int F; int c; };
+#define NORM_BATCH 16
+#define ACC_TPB 128
+
+template <class C> struct LaunchHot {
+    static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
+                       int c, int W, int F, uint32_t *counters, uint32_t *refs);
+    static void accumulate(cudaStream_t st, uint32_t max_pieces, const affine_t *tables, const uint32_t *refs, const uint32_t *order,
+                           const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res);
+};
+template <class C> struct LaunchCold {
+    // mode 0: level 0 (through the piece table), 1: direct (S and T), 2: sum only
+    static void reduce_slices(int mode, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t m, xyzz_t *outS, xyzz_t *outT);
+    static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, int extra_n, const xyzz_t *extra);
+    static void double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp);
+    static void batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst);
+    static void gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp);
+    static void gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out);
+    static void test_fp(int op, const fp *a, const fp *b, fp *r, uint32_t n);
+    static void test_ec(int op, xyzz_t *acc, const void *other, uint32_t n, int reps);
+};
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+}  // namespace b200msm

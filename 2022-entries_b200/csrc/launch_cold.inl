@@ -1,0 +1,38 @@
+// launch_cold.inl -- definitions of LaunchCold<C>; included by inst_cold_*.cu which instantiate one curve each.
+#include "launch.h"
+#include "kernels_cold.cuh"
+
+namespace b200msm {
+
+template <class C>
+void LaunchCold<C>::reduce_slices(int mode, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t m, xyzz_t *outS, xyzz_t *outT) {
+    uint32_t blocks = cdiv(n_out, 128);
+    if (mode == 0) k_reduce_slices<C, true, false><<<blocks, 128, 0, st>>>(in, piece_off, n_out, m, outS, outT);
+    else if (mode == 1) k_reduce_slices<C, false, false><<<blocks, 128, 0, st>>>(in, nullptr, n_out, m, outS, outT);
+    else k_reduce_slices<C, false, true><<<blocks, 128, 0, st>>>(in, nullptr, n_out, m, outS, nullptr);
+}
+template <class C>
+void LaunchCold<C>::finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, int extra_n, const xyzz_t *extra) {
+    k_finalize<C><<<1, 32, 0, st>>>(a, out_xyzz, out_jac, extra_n, extra);
+}
+template <class C> void LaunchCold<C>::double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp) {
+    k_double_n<C><<<cdiv(n, 128), 128, 0, st>>>(src, n, k, tmp);
+}
+template <class C> void LaunchCold<C>::batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst) {
+    k_batch_normalize<C><<<cdiv(cdiv(n, NORM_BATCH), 128), 128, 0, st>>>(tmp, n, dst);
+}
+template <class C>
+void LaunchCold<C>::gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp) {
+    k_gen_points<C><<<cdiv(n, 128), 128, 0, st>>>(first, n, seed, mode, distinct, gx, gy, tmp);
+}
+template <class C> void LaunchCold<C>::gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out) {
+    k_gen_scalars<C><<<cdiv(n, 256), 256, 0, st>>>(n, seed, out);
+}
+template <class C> void LaunchCold<C>::test_fp(int op, const fp *a, const fp *b, fp *r, uint32_t n) {
+    k_test_fp<C><<<cdiv(n, 128), 128>>>(op, a, b, r, n);
+}
+template <class C> void LaunchCold<C>::test_ec(int op, xyzz_t *acc, const void *other, uint32_t n, int reps) {
+    k_test_ec<C><<<cdiv(n, 64), 64>>>(op, acc, other, n, reps);
+}
+
+}  // namespace b200msm

@@ -1,0 +1,632 @@
+// msm.cu -- host orchestrator and C ABI of libb200msm.so (include/b200msm.h).
+//
+// Stands in for the reference's L3 layer: yrrid MSMContext (MSM.cu:139-503), sppark
+// pippenger_t + pippenger_inf.cu, matter-labs msm.cu schedule_execution.  One context = one device, one set of
+// base tables, one stream; every MSM is the fixed kernel sequence in run_msm() below.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/b200msm.h"
+#include "kernels_common.cuh"
+#include "launch.h"
+
+using namespace b200msm;
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return ctx->fail((int)e__, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+struct red_step_t {
+    bool indirect, sum_only;
+    const xyzz_t *in;
+    uint32_t n_out, m;
+    xyzz_t *outS, *outT;
+};
+
+struct b200msm_ctx {
+    int curve = 0, device = 0;
+    int req_c = 0, req_tables = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    int sticky = 0;
+
+    // plan
+    uint64_t n = 0;
+    int c = 0, W = 0, T = 0, F = 0;
+    uint32_t nbuckets = 0, lmax = 0, max_pieces = 0;
+    uint64_t max_refs = 0;
+    int launches = 0;
+
+    // device memory
+    affine_t *tables = nullptr;
+    uint32_t *infmask = nullptr;
+    uint32_t *counts = nullptr, *bucket_off = nullptr, *cursor = nullptr, *piece_off = nullptr;
+    uint32_t *piece_start = nullptr, *piece_len = nullptr, *order = nullptr, *len_hist = nullptr, *len_cursor = nullptr;
+    uint32_t *scan_tmp = nullptr, *refs = nullptr;
+    xyzz_t *res = nullptr, *red_buf = nullptr, *part_xyzz = nullptr;
+    uint8_t *scal_buf[2] = {nullptr, nullptr};
+    uint8_t *out_dev = nullptr;      // batches x 144
+    uint64_t out_dev_cap = 0;
+    std::vector<red_step_t> red_steps;
+    fin_args_t fin;
+    cudaEvent_t ev[7] = {};
+    cudaEvent_t ev_copied[2] = {}, ev_free[2] = {};
+
+    int fail(int code, const std::string &msg) {
+        err = msg;
+        if (code > 0) sticky = code;
+        fprintf(stderr, "b200msm: %s\n", msg.c_str());
+        return code;
+    }
+    void free_plan() {
+        void *ptrs[] = {tables, infmask, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
+                        scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1]};
+        for (void *p : ptrs) if (p) cudaFree(p);
+        tables = nullptr; infmask = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
+        scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr;
+        red_steps.clear();
+        n = 0;
+    }
+};
+
+static int scalar_bits(int curve) { return curve == 0 ? Bls12_377::SCALAR_BITS : Bls12_381::SCALAR_BITS; }
+
+// ---------------------------------------------------------------------------------------------
+// window plan: choose c (window bits), T (tables) and F (folded windows) for n points.
+// cost model: W*n mixed adds (10 modmul) + 2 full adds (14 modmul) per bucket, buckets = F * 2^(c-1);
+// T limited by device memory (96 n bytes per table) and by the 31-bit point reference (T*n < 2^31).
+static void choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
+    const int sb = scalar_bits(ctx->curve);
+    uint64_t tmax_mem = (uint64_t)((double)free_bytes * 0.55 / (96.0 * (double)n));
+    uint64_t tmax_ref = ((1ull << 31) - 1) / n;
+    uint64_t tmax = tmax_mem < tmax_ref ? tmax_mem : tmax_ref;
+    if (tmax < 1) tmax = 1;
+    if (ctx->req_tables > 0 && (uint64_t)ctx->req_tables < tmax) tmax = ctx->req_tables;
+    int best_c = 0;
+    double best = 1e300;
+    int lo = ctx->req_c > 0 ? ctx->req_c : 4, hi = ctx->req_c > 0 ? ctx->req_c : 24;
+    for (int c = lo; c <= hi; c++) {
+        int W = (sb + c - 1) / c;
+        int T = (int)(tmax < (uint64_t)W ? tmax : W);
+        int F = (W + T - 1) / T;
+        double buckets = (double)F * (double)(1ull << (c - 1));
+        if (buckets > (double)(1u << 27)) continue;
+        double red = 28.0 * buckets;
+        double cost = 10.0 * (double)W * (double)n + red;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    ctx->c = best_c;
+    ctx->W = (sb + best_c - 1) / best_c;
+    int T = (int)(tmax < (uint64_t)ctx->W ? tmax : ctx->W);
+    ctx->F = (ctx->W + T - 1) / T;
+    ctx->T = (ctx->W + ctx->F - 1) / ctx->F;
+    ctx->nbuckets = (uint32_t)ctx->F << (ctx->c - 1);
+}
+
+template <class T> static cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
+
+static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
+    ctx->free_plan();
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    choose_plan(ctx, n, free_b);
+    ctx->n = n;
+    ctx->max_refs = (uint64_t)ctx->W * n;
+    if (ctx->max_refs >= (1ull << 32)) return ctx->fail(-1, "too many point references for 32-bit list offsets");
+    // Lmax: uniform scalars give ~W*n/buckets points per bucket; pieces only split buckets far above that
+    uint64_t mean = ctx->max_refs / ctx->nbuckets + 1;
+    uint32_t lmax = 256;
+    while (lmax < 4 * mean && lmax < 4096) lmax <<= 1;
+    ctx->lmax = lmax;
+    ctx->max_pieces = ctx->nbuckets + (uint32_t)(ctx->max_refs / lmax) + 1;
+    const uint32_t nb = ctx->nbuckets;
+    CK(dmalloc(&ctx->tables, (size_t)ctx->T * n));
+    CK(dmalloc(&ctx->infmask, (size_t)cdiv(n, 32) + 1));
+    CK(dmalloc(&ctx->counts, (size_t)nb + 1));
+    CK(dmalloc(&ctx->bucket_off, (size_t)nb + 1));
+    CK(dmalloc(&ctx->cursor, (size_t)nb + 1));
+    CK(dmalloc(&ctx->piece_off, (size_t)nb + 1));
+    CK(dmalloc(&ctx->piece_start, (size_t)ctx->max_pieces));
+    CK(dmalloc(&ctx->piece_len, (size_t)ctx->max_pieces));
+    CK(dmalloc(&ctx->order, (size_t)ctx->max_pieces));
+    CK(dmalloc(&ctx->len_hist, (size_t)lmax + 1));
+    CK(dmalloc(&ctx->len_cursor, (size_t)lmax + 1));
+    CK(dmalloc(&ctx->scan_tmp, (size_t)cdiv(nb, SCAN_TPB * SCAN_EPT) + 2));
+    CK(dmalloc(&ctx->refs, (size_t)ctx->max_refs + 1));
+    CK(dmalloc(&ctx->res, (size_t)ctx->max_pieces));
+    CK(dmalloc(&ctx->part_xyzz, 1));
+
+    // bucket-reduction plan (see k_reduce_slices): sizes first, then carve red_buf
+    struct lvl { uint32_t n_in, m, n_out; };
+    std::vector<lvl> main_lv;
+    uint32_t per_f = 1u << (ctx->c - 1);
+    {
+        uint32_t cur = per_f;
+        bool first = true;
+        while (first || cur > 32) {
+            uint32_t m = cur / 32; if (m > 64) m = 64; if (m < 1) m = 1;
+            main_lv.push_back({cur, m, cur / m});
+            cur /= m;
+            first = false;
+        }
+    }
+    size_t need = 0;
+    for (auto &l : main_lv) {
+        need += 2 * (size_t)l.n_out;          // S and T
+        uint32_t t = l.n_out;
+        while (t > 32) { uint32_t m = t / 32; if (m > 64) m = 64; t /= m; need += t; }
+    }
+    need *= ctx->F;
+    CK(dmalloc(&ctx->red_buf, need + 1));
+    xyzz_t *bump = ctx->red_buf;
+    auto take = [&](size_t cnt) { xyzz_t *p = bump; bump += cnt; return p; };
+    ctx->red_steps.clear();
+    fin_args_t &fin = ctx->fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.F = ctx->F; fin.c = ctx->c;
+    const uint32_t F = ctx->F;
+    const xyzz_t *cur_arr = ctx->res;
+    uint32_t shift = 0;
+    struct pend { xyzz_t *arr; uint32_t n; uint32_t shift; };
+    std::vector<pend> pending;
+    for (size_t li = 0; li < main_lv.size(); li++) {
+        lvl &l = main_lv[li];
+        xyzz_t *S = take((size_t)F * l.n_out), *Tt = take((size_t)F * l.n_out);
+        ctx->red_steps.push_back({li == 0, false, cur_arr, F * l.n_out, l.m, S, Tt});
+        pending.push_back({Tt, l.n_out, shift});
+        uint32_t lg = 0; while ((1u << lg) < l.m) lg++;
+        shift += lg;
+        cur_arr = S;
+    }
+    uint32_t last_n = main_lv.back().n_out;
+    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, 0, 0};          // sum of all buckets
+    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, shift, 1};      // 2^shift * W0(S_last)
+    for (auto &p : pending) {
+        xyzz_t *arr = p.arr; uint32_t t = p.n;
+        while (t > 32) {
+            uint32_t m = t / 32; if (m > 64) m = 64;
+            xyzz_t *o = take((size_t)F * (t / m));
+            ctx->red_steps.push_back({false, true, arr, F * (t / m), m, o, nullptr});
+            arr = o; t /= m;
+        }
+        if (fin.nterms >= FIN_MAX_TERMS) return ctx->fail(-1, "reduction plan has too many terms");
+        fin.term[fin.nterms++] = {arr, t, t, p.shift, 0};
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class C> static int build_tables_t(b200msm_ctx *ctx) {
+    // tables[j] = 2^(c*F) * tables[j-1], normalised to affine; chunked so the XYZZ scratch stays small
+    const uint32_t n = (uint32_t)ctx->n;
+    const uint32_t chunk = 1u << 22;
+    xyzz_t *tmp = nullptr;
+    uint32_t tn = n < chunk ? n : chunk;
+    CK(dmalloc(&tmp, tn));
+    for (int j = 1; j < ctx->T; j++) {
+        for (uint32_t first = 0; first < n; first += chunk) {
+            uint32_t cnt = n - first < chunk ? n - first : chunk;
+            const affine_t *src = ctx->tables + (size_t)(j - 1) * n + first;
+            affine_t *dst = ctx->tables + (size_t)j * n + first;
+            LaunchCold<C>::double_n(ctx->stream, src, cnt, ctx->c * ctx->F, tmp);
+            LaunchCold<C>::batch_normalize(ctx->stream, tmp, cnt, dst);
+        }
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    return 0;
+}
+static int build_tables(b200msm_ctx *ctx) { return ctx->curve == 0 ? build_tables_t<Bls12_377>(ctx) : build_tables_t<Bls12_381>(ctx); }
+
+template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int mode, uint64_t distinct, const fp &gx, const fp &gy) {
+    const uint32_t n = (uint32_t)ctx->n;
+    uint32_t gen_n = mode == 0 ? (uint32_t)(distinct < n ? distinct : n) : n;
+    const uint32_t chunk = 1u << 22;
+    xyzz_t *tmp = nullptr;
+    CK(dmalloc(&tmp, gen_n < chunk ? gen_n : chunk));
+    for (uint32_t first = 0; first < gen_n; first += chunk) {
+        uint32_t cnt = gen_n - first < chunk ? gen_n - first : chunk;
+        LaunchCold<C>::gen_points(ctx->stream, first, cnt, seed, mode, (uint32_t)(distinct ? distinct : 1), gx, gy, tmp);
+        LaunchCold<C>::batch_normalize(ctx->stream, tmp, cnt, ctx->tables + first);
+    }
+    if (gen_n < n) {
+        uint64_t work = (uint64_t)(n - gen_n) * 6;
+        k_replicate<<<cdiv(work, 256), 256, 0, ctx->stream>>>(ctx->tables, gen_n, n);
+    }
+    CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+    return 0;
+}
+
+// generator in Montgomery form (P1B/nickray/driver/bls12-377/src/curves/g1.rs:159-165)
+static void generator(int curve, fp &gx, fp &gy) {
+    static const uint32_t g377x[12] = {0xb21be9efu, 0xeab9b16eu, 0xffcd394eu, 0xd5481512u, 0xbd37cb5cu, 0x188282c8u, 0xaa9d41bbu, 0x85951e2cu, 0xbf87ff54u, 0xc8fc6225u, 0xfe740a67u, 0x008848deu};
+    static const uint32_t g377y[12] = {0x559c8ea6u, 0xfd82de55u, 0x34a9591au, 0xc2fe3d36u, 0x4fb82305u, 0x6d182ad4u, 0xca3e52d9u, 0xbd7fb348u, 0x30afeec4u, 0x1f674f5du, 0xc5102effu, 0x01914a69u};
+    static const uint32_t g381x[12] = {0xdb22c6bbu, 0xfb3af00au, 0xf97a1aefu, 0x6c55e83fu, 0x171bac58u, 0xa14e3a3fu, 0x9774b905u, 0xc3688c4fu, 0x4fa9ac0fu, 0x2695638cu, 0x3197d794u, 0x17f1d3a7u};
+    static const uint32_t g381y[12] = {0x46c5e7e1u, 0x0caa2329u, 0xa2888ae4u, 0xd03cc744u, 0x2c04b3edu, 0x00db18cbu, 0xd5d00af6u, 0xfcf5e095u, 0x741d8ae4u, 0xa09e30edu, 0xe3aaa0f1u, 0x08b3f481u};
+    // canonical -> Montgomery on the host (schoolbook, only here): x * 2^384 mod p by 384 modular doublings
+    auto to_mont = [&](const uint32_t *v, fp &out) {
+        uint32_t a[13];
+        for (int i = 0; i < 12; i++) a[i] = v[i];
+        a[12] = 0;
+        auto p = [&](int i) { return curve == 0 ? Bls12_377::p(i) : Bls12_381::p(i); };
+        for (int s = 0; s < 384; s++) {
+            uint32_t carry = 0;
+            for (int i = 0; i < 13; i++) { uint32_t nc = a[i] >> 31; a[i] = (a[i] << 1) | carry; carry = nc; }
+            // a >= p ? a -= p
+            bool ge = a[12] != 0;
+            if (!ge) { ge = true; for (int i = 11; i >= 0; i--) if (a[i] != p(i)) { ge = a[i] > p(i); break; } }
+            if (ge) { uint64_t br = 0; for (int i = 0; i < 12; i++) { uint64_t t = (uint64_t)a[i] - p(i) - br; a[i] = (uint32_t)t; br = (t >> 32) & 1; } a[12] -= (uint32_t)br; }
+        }
+        for (int i = 0; i < 12; i++) out.l[i] = a[i];
+    };
+    to_mont(curve == 0 ? g377x : g381x, gx);
+    to_mont(curve == 0 ? g377y : g381y, gy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one MSM on the context's stream.  scalars: device, n x 32 bytes.  Exactly one of out_jac / out_xyzz is set.
+template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz, bool hist_done) {
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->n, nb = ctx->nbuckets, lmax = ctx->lmax;
+    const uint32_t *sc = (const uint32_t *)scalars_dev;
+    int launches = 0;
+    cudaEventRecord(ctx->ev[0], st);
+    if (!hist_done) {
+        CK(cudaMemsetAsync(ctx->counts, 0, ((size_t)nb + 1) * 4, st));
+        LaunchHot<C>::digits(0, st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->counts, nullptr);
+        launches++;
+    }
+    cudaEventRecord(ctx->ev[1], st);
+    // bucket offsets (and scatter cursors), then scatter the point references
+    const uint32_t sblocks = cdiv(nb, SCAN_TPB * SCAN_EPT);
+    k_scan_block_sums<0><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp);
+    k_scan_top<<<1, 1024, 0, st>>>(ctx->scan_tmp, sblocks);
+    k_scan_apply<0><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, ctx->bucket_off, ctx->cursor);
+    LaunchHot<C>::digits(1, st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->cursor, ctx->refs);
+    launches += 4;
+    cudaEventRecord(ctx->ev[2], st);
+    // pieces
+    k_scan_block_sums<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp);
+    k_scan_top<<<1, 1024, 0, st>>>(ctx->scan_tmp, sblocks);
+    k_scan_apply<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, ctx->piece_off, nullptr);
+    CK(cudaMemsetAsync(ctx->len_hist, 0, ((size_t)lmax + 1) * 4, st));
+    const size_t hist_smem = ((size_t)lmax + 1) * 4;
+    k_piece_fill<<<cdiv(nb, PIECE_TPB), PIECE_TPB, hist_smem, st>>>(ctx->bucket_off, ctx->piece_off, nb, lmax, ctx->piece_start, ctx->piece_len, ctx->len_hist);
+    k_piece_len_scan<<<1, 1024, 0, st>>>(ctx->len_hist, lmax, ctx->len_cursor);
+    const uint32_t *npieces_ptr = ctx->piece_off + nb;
+    k_piece_order<<<cdiv(ctx->max_pieces, PIECE_TPB), PIECE_TPB, hist_smem, st>>>(ctx->piece_len, npieces_ptr, lmax, ctx->len_cursor, ctx->order);
+    launches += 6;
+    cudaEventRecord(ctx->ev[3], st);
+    // the hot loop
+    LaunchHot<C>::accumulate(st, ctx->max_pieces, ctx->tables, ctx->refs, ctx->order, ctx->piece_start, ctx->piece_len, npieces_ptr, ctx->res);
+    launches++;
+    cudaEventRecord(ctx->ev[4], st);
+    // bucket reduction
+    for (const red_step_t &s : ctx->red_steps) {
+        LaunchCold<C>::reduce_slices(s.indirect ? 0 : (s.sum_only ? 2 : 1), st, s.in, ctx->piece_off, s.n_out, s.m, s.outS, s.outT);
+        launches++;
+    }
+    cudaEventRecord(ctx->ev[5], st);
+    LaunchCold<C>::finalize(st, ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac, 0, nullptr);
+    launches++;
+    cudaEventRecord(ctx->ev[6], st);
+    ctx->launches = launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz, bool hist_done = false) {
+    return ctx->curve == 0 ? run_msm_t<Bls12_377>(ctx, scalars_dev, out_jac, out_xyzz, hist_done)
+                           : run_msm_t<Bls12_381>(ctx, scalars_dev, out_jac, out_xyzz, hist_done);
+}
+
+static int check_ctx(b200msm_ctx *ctx) {
+    if (!ctx) return -1;
+    if (ctx->sticky) return ctx->sticky;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ctx->fail((int)e, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, int tables) {
+    if (!out || (curve != 0 && curve != 1) || window_bits < 0 || window_bits > 26 || (window_bits > 0 && window_bits < 2) || tables < 0) {
+        g_create_error = "b200msm_create: bad argument";
+        return -1;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("b200msm_create: no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path";
+        fprintf(stderr, "%s\n", g_create_error.c_str());
+        return -2;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "b200msm_create: bad device index"; return -1; }
+    b200msm_ctx *ctx = new b200msm_ctx();
+    ctx->curve = curve; ctx->device = device; ctx->req_c = window_bits; ctx->req_tables = tables;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming); }
+    if (e != cudaSuccess) {
+        g_create_error = std::string("b200msm_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return (int)e;
+    }
+    *out = ctx;
+    return 0;
+}
+
+int b200msm_destroy(b200msm_ctx *ctx) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->free_plan();
+    if (ctx->out_dev) cudaFree(ctx->out_dev);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return 0;
+}
+
+const char *b200msm_last_error(const b200msm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cuda_stream) {
+        if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else if (!ctx->own_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return 0;
+}
+
+int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!affine_host || n == 0 || n >= (1ull << 31) || stride < 96 || (stride & 7)) return ctx->fail(-1, "b200msm_set_bases: bad argument");
+    rc = alloc_plan(ctx, n); if (rc) return rc;
+    // stage the arkworks records through device memory in chunks
+    const uint64_t chunk = 1ull << 22;
+    uint8_t *raw = nullptr;
+    CK(cudaMalloc((void **)&raw, (size_t)((n < chunk ? n : chunk) * stride)));
+    CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
+    for (uint64_t first = 0; first < n; first += chunk) {
+        uint64_t cnt = n - first < chunk ? n - first : chunk;
+        CK(cudaMemcpyAsync(raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), cudaMemcpyHostToDevice, ctx->stream));
+        k_convert_points<<<cdiv(cnt, 256), 256, 0, ctx->stream>>>(raw, (uint32_t)cnt, (uint32_t)stride, ctx->tables + first, ctx->infmask + first / 32);
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(raw);
+    return build_tables(ctx);
+}
+
+int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int mode, uint64_t distinct) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (n == 0 || n >= (1ull << 31) || (mode != 0 && mode != 1) || (mode == 0 && distinct == 0) || (mode == 1 && seed == 0))
+        return ctx->fail(-1, "b200msm_set_bases_generated: bad argument");
+    rc = alloc_plan(ctx, n); if (rc) return rc;
+    fp gx, gy;
+    generator(ctx->curve, gx, gy);
+    rc = ctx->curve == 0 ? gen_bases_t<Bls12_377>(ctx, seed, mode, distinct, gx, gy) : gen_bases_t<Bls12_381>(ctx, seed, mode, distinct, gx, gy);
+    if (rc) return rc;
+    return build_tables(ctx);
+}
+
+int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uint64_t n) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!affine96_host || first + n > ctx->n) return ctx->fail(-1, "b200msm_get_bases: bad argument");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(affine96_host, ctx->tables + first, (size_t)n * 96, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int b200msm_generate_scalars(b200msm_ctx *ctx, void *scalars_dev, uint64_t n, uint64_t seed) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_dev || n == 0 || n >= (1ull << 32)) return ctx->fail(-1, "b200msm_generate_scalars: bad argument");
+    if (ctx->curve == 0) LaunchCold<Bls12_377>::gen_scalars(ctx->stream, (uint32_t)n, seed, (uint32_t *)scalars_dev);
+    else LaunchCold<Bls12_381>::gen_scalars(ctx->stream, (uint32_t)n, seed, (uint32_t *)scalars_dev);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200msm_msm_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_jacobian_dev) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_dev || !out_jacobian_dev || ctx->n == 0 || n != ctx->n) return ctx->fail(-1, "b200msm_msm_device: bad argument (bases not set or length mismatch)");
+    return run_msm(ctx, scalars_dev, out_jacobian_dev, nullptr);
+}
+
+int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_dev || !out_xyzz_dev || ctx->n == 0 || n != ctx->n) return ctx->fail(-1, "b200msm_msm_partial_device: bad argument");
+    return run_msm(ctx, scalars_dev, nullptr, out_xyzz_dev);
+}
+
+int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!xyzz_dev || count < 1 || !out_jacobian_dev) return ctx->fail(-1, "b200msm_combine_device: bad argument");
+    fin_args_t fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.F = 0; fin.c = 1;
+    if (ctx->curve == 0) LaunchCold<Bls12_377>::finalize(ctx->stream, fin, nullptr, (uint32_t *)out_jacobian_dev, count, (const xyzz_t *)xyzz_dev);
+    else LaunchCold<Bls12_381>::finalize(ctx->stream, fin, nullptr, (uint32_t *)out_jacobian_dev, count, (const xyzz_t *)xyzz_dev);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uint64_t batches, void *out_jacobian_host) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_host || !out_jacobian_host || ctx->n == 0 || n != ctx->n || batches == 0) return ctx->fail(-1, "b200msm_msm_host: bad argument (bases not set or length mismatch)");
+    const size_t bytes = (size_t)n * 32;
+    for (int i = 0; i < 2; i++) if (!ctx->scal_buf[i] && (i == 0 || batches > 1)) CK(cudaMalloc((void **)&ctx->scal_buf[i], bytes));
+    if (ctx->out_dev_cap < batches) {
+        if (ctx->out_dev) cudaFree(ctx->out_dev);
+        CK(cudaMalloc((void **)&ctx->out_dev, (size_t)batches * 144));
+        ctx->out_dev_cap = batches;
+    }
+    // the caller's stream may hold earlier work on these buffers
+    CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+    for (uint64_t b = 0; b < batches; b++) {
+        int k = (int)(b & 1);
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[k], 0));
+        CK(cudaMemcpyAsync(ctx->scal_buf[k], (const uint8_t *)scalars_host + b * bytes, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));
+        rc = run_msm(ctx, ctx->scal_buf[k], ctx->out_dev + b * 144, nullptr);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_free[k], ctx->stream));
+    }
+    CK(cudaMemcpyAsync(out_jacobian_host, ctx->out_dev, (size_t)batches * 144, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200msm_sync(b200msm_ctx *ctx) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]) {
+    if (!ctx || !info) return -1;
+    info[0] = ctx->n; info[1] = ctx->c; info[2] = ctx->W; info[3] = ctx->T; info[4] = ctx->F; info[5] = ctx->nbuckets; info[6] = ctx->lmax; info[7] = ctx->launches;
+    return 0;
+}
+
+int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!stage_ms) return -1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(&stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return 0;
+}
+
+// ---- element-wise test entry points ----------------------------------------------------------
+static int test_fail(const char *what, cudaError_t e) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    fprintf(stderr, "b200msm: %s\n", g_create_error.c_str());
+    return (int)e;
+}
+#define TCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return test_fail(#call, e__); } while (0)
+
+int b200msm_test_fp_op(int curve, int op, const void *a, const void *b, void *r, uint64_t n) {
+    if (!a || !b || !r || n == 0 || (curve != 0 && curve != 1)) return -1;
+    fp *da, *db, *dr;
+    size_t bytes = (size_t)n * 48;
+    TCK(cudaMalloc((void **)&da, bytes)); TCK(cudaMalloc((void **)&db, bytes)); TCK(cudaMalloc((void **)&dr, bytes));
+    TCK(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice)); TCK(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
+    if (curve == 0) LaunchCold<Bls12_377>::test_fp(op, da, db, dr, (uint32_t)n);
+    else LaunchCold<Bls12_381>::test_fp(op, da, db, dr, (uint32_t)n);
+    TCK(cudaGetLastError());
+    TCK(cudaMemcpy(r, dr, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dr);
+    return 0;
+}
+
+int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t n, int reps) {
+    if (!acc || n == 0 || (curve != 0 && curve != 1) || op < 0 || op > 3 || (op != 2 && !other)) return -1;
+    xyzz_t *dacc; void *doth = nullptr;
+    size_t ob = (op == 1 ? 192 : 96) * (size_t)n;
+    TCK(cudaMalloc((void **)&dacc, (size_t)n * 192));
+    TCK(cudaMemcpy(dacc, acc, (size_t)n * 192, cudaMemcpyHostToDevice));
+    if (op != 2) { TCK(cudaMalloc(&doth, ob)); TCK(cudaMemcpy(doth, other, ob, cudaMemcpyHostToDevice)); }
+    if (curve == 0) LaunchCold<Bls12_377>::test_ec(op, dacc, doth, (uint32_t)n, reps);
+    else LaunchCold<Bls12_381>::test_ec(op, dacc, doth, (uint32_t)n, reps);
+    TCK(cudaGetLastError());
+    TCK(cudaMemcpy(acc, dacc, (size_t)n * 192, cudaMemcpyDeviceToHost));
+    cudaFree(dacc); if (doth) cudaFree(doth);
+    return 0;
+}
+
+// ---- Family A (sppark) -----------------------------------------------------------------------
+static RustError rust_error(int code, const char *msg) {
+    RustError e;
+    e.code = code;
+    e.message = (code != 0 && msg) ? strdup(msg) : nullptr;
+    return e;
+}
+
+RustError mult_pippenger_init(MultiScalarMultContext *context, const void *points_with_infinity, size_t npoints, size_t ffi_affine_sz) {
+    if (!context) return rust_error(-1, "mult_pippenger_init: null context");
+    context->context = nullptr;
+    b200msm_ctx *ctx = nullptr;
+    int rc = b200msm_create(&ctx, B200MSM_BLS12_377, 0, 0, 0);
+    if (rc) return rust_error(rc, b200msm_last_error(nullptr));
+    rc = b200msm_set_bases(ctx, points_with_infinity, npoints, ffi_affine_sz);
+    if (rc) { RustError e = rust_error(rc, b200msm_last_error(ctx)); b200msm_destroy(ctx); return e; }
+    context->context = ctx;
+    return rust_error(0, nullptr);
+}
+
+RustError mult_pippenger_inf(MultiScalarMultContext *context, uint64_t *out, const void *points_with_infinity, size_t npoints, size_t batch_size,
+                             const void *scalars, size_t ffi_affine_sz) {
+    (void)points_with_infinity; (void)ffi_affine_sz;    // bases were taken at init, exactly as in the reference
+    if (!context || !context->context) return rust_error(-1, "mult_pippenger_inf: context not initialised");
+    b200msm_ctx *ctx = (b200msm_ctx *)context->context;
+    int rc = b200msm_msm_host(ctx, scalars, npoints, batch_size, out);
+    if (rc) return rust_error(rc, b200msm_last_error(ctx));
+    return rust_error(0, nullptr);
+}
+
+RustError mult_pippenger_free(MultiScalarMultContext *context) {
+    if (!context || !context->context) return rust_error(-1, "mult_pippenger_free: context not initialised");
+    b200msm_destroy((b200msm_ctx *)context->context);
+    context->context = nullptr;
+    return rust_error(0, nullptr);
+}
+
+// ---- Family B (yrrid) ------------------------------------------------------------------------
+struct yrrid_ctx_t { b200msm_ctx *ctx; int32_t max_points, max_batches; uint32_t points; };
+
+void *MSMAllocContext(int32_t maxPoints, int32_t maxBatches) {
+    if (maxPoints <= 0 || maxBatches <= 0) return nullptr;
+    b200msm_ctx *ctx = nullptr;
+    if (b200msm_create(&ctx, B200MSM_BLS12_377, 0, 0, 0) != 0) return nullptr;
+    yrrid_ctx_t *y = new yrrid_ctx_t{ctx, maxPoints, maxBatches, 0};
+    return y;
+}
+int32_t MSMFreeContext(void *context) {
+    if (!context) return -1;
+    yrrid_ctx_t *y = (yrrid_ctx_t *)context;
+    b200msm_destroy(y->ctx);
+    delete y;
+    return 0;
+}
+int32_t MSMPreprocessPoints(void *context, void *affinePointsPtr, uint32_t points) {
+    if (!context) return -1;
+    yrrid_ctx_t *y = (yrrid_ctx_t *)context;
+    if (points == 0 || (int64_t)points > (int64_t)y->max_points) return -1;
+    int rc = b200msm_set_bases(y->ctx, affinePointsPtr, points, 104);
+    if (rc == 0) y->points = points;
+    return rc;
+}
+int32_t MSMRun(void *context, uint64_t *projectiveResultsPtr, void *scalarsPtr, uint32_t scalars) {
+    if (!context) return -1;
+    yrrid_ctx_t *y = (yrrid_ctx_t *)context;
+    if (y->points == 0 || scalars == 0 || scalars % y->points != 0) return -1;
+    uint32_t batches = scalars / y->points;
+    if ((int64_t)batches > (int64_t)y->max_batches) return -1;
+    return b200msm_msm_host(y->ctx, scalarsPtr, y->points, batches, projectiveResultsPtr);
+}
+
+}  // extern "C"

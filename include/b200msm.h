@@ -1,0 +1,109 @@
+/*
+ * b200msm.h -- C ABI of libb200msm.so: BLS12-377 / BLS12-381 G1 multi-scalar multiplication on B200 (sm_100a).
+ *
+ * This is the drop-in seam of the ZPrize-2022 prize-1a harness.  Paths below are relative
+ * to the reference tree, P1A = open-division/prize1-msm/prize1a-msm-gpu.  Three groups of symbols:
+ *
+ *   1. Family A -- the organisers' (sppark) FFI, bound by P1A/storswiftlabs/src/lib.rs:18-41 and implemented in the
+ *      reference by P1A/storswiftlabs/cuda/pippenger_inf.cu:51-173.
+ *   2. Family B -- the yrrid / combined-top-solutions FFI, bound by P1A/yrrid/src/lib.rs:22-36, declared in
+ *      P1A/yrrid/yrrid-msm/MSM.h:65-76.
+ *   3. b200msm_* -- the native interface both families are thin adapters over (adds what the reference lacks:
+ *      a destroy call, device-resident scalars, per-GPU partial results for point sharding, stage timings).
+ *
+ * Data layouts are arkworks' in-memory ones (P1B/hardcaml/.../rust_types.h:73-83, yrrid MSM.cu:93-95,378):
+ *   G1Affine      104 bytes: x, y = 6 x u64 little-endian Montgomery (R = 2^384), u8 infinity flag at offset 96
+ *   scalar         32 bytes: 4 x u64 little-endian integer in [0, r), used as-is (not Montgomery-converted)
+ *   G1Projective  144 bytes: Jacobian x, y, z (x/z^2, y/z^3); this library returns (x_affine, y_affine, 1) or the
+ *                            arkworks zero (1, 1, 0) -- any representative is valid, the harness compares projectively
+ *
+ * All functions return 0 on success; -1 = bad argument, -2 = CUDA extension unusable (no device), any positive value
+ * is a cudaError_t.  After a failure b200msm_last_error() describes it.  A context is used from one thread at a
+ * time (the harness calls multi_scalar_mult repeatedly on the same context from one thread).
+ */
+#ifndef B200MSM_H
+#define B200MSM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- 3. native interface ------------------------------------------------------------------------------------ */
+typedef struct b200msm_ctx b200msm_ctx;
+
+enum { B200MSM_BLS12_377 = 0, B200MSM_BLS12_381 = 1 };
+enum { B200MSM_BASES_HARNESS = 0, B200MSM_BASES_DISTINCT = 1 };
+
+/* window_bits = 0 and tables = 0 select the size-tuned plan (see DESIGN.md "window plan"). */
+int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, int tables);
+int b200msm_destroy(b200msm_ctx *ctx);
+const char *b200msm_last_error(const b200msm_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
+
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
+int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream);
+
+/* multi_scalar_mult_init: upload `n` arkworks G1Affine records (stride bytes apart, 96 <= stride; the infinity
+ * flag is read only when stride > 96) and build the base tables 2^(c*F*j) * P_i.  Replaces
+ * mult_pippenger_init / MSMPreprocessPoints + precomputePointsKernel (P1A/yrrid/yrrid-msm/PrecomputePoints.cu:10-39). */
+int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride);
+
+/* Synthetic bases with known discrete logs, generated on the device (tests and bench.py; 2^26 arkworks records
+ * would be 6.5 GiB of host traffic).  HARNESS: `distinct` random multiples of the generator replicated to n, the
+ * shape of the reference generator (P1A/yrrid/src/util.rs:15-28); DISTINCT: (seed + i) * G.                  */
+int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int mode, uint64_t distinct);
+/* Copy base table 0 back as n x 96-byte (x, y) records (tests). */
+int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uint64_t n);
+
+/* Uniform scalars in [0, r) written to device memory (n x 32 bytes). */
+int b200msm_generate_scalars(b200msm_ctx *ctx, void *scalars_dev, uint64_t n, uint64_t seed);
+
+/* multi_scalar_mult, one batch, scalars already in device memory.  Asynchronous on the context's stream: the
+ * 144-byte Jacobian result is written to out_dev (device memory) when the stream reaches it. */
+int b200msm_msm_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_jacobian_dev);
+/* Same, scalars and result in host memory (pinned or pageable); `batches` results of 144 bytes; returns after the
+ * results are in place.  Scalar upload of batch b+1 overlaps the compute of batch b. */
+int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uint64_t batches, void *out_jacobian_host);
+
+/* Point sharding across GPUs: the local shard's sum as one 192-byte XYZZ record in device memory (asynchronous),
+ * and the combine step run after the all-gather: sum `count` XYZZ records -> 144-byte Jacobian (device memory). */
+int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev);
+int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev);
+
+int b200msm_sync(b200msm_ctx *ctx);
+
+/* Plan and measurements of the last run.  info[0..7] = n, window bits c, windows W, tables T, folded windows F,
+ * buckets, Lmax, kernel launches of the last MSM.  stage_ms[0..5] = digits+histogram, scan+scatter, pieces,
+ * accumulate, bucket reduce, finalize (CUDA events on the context's stream; valid after b200msm_sync). */
+int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]);
+int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]);
+
+/* Element-wise device arithmetic on host arrays, for the parity tests of the field and curve layers.
+ * fp op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 to-Montgomery, 6 from-Montgomery (48-byte elements, canonical out).
+ * ec op: 0 acc += affine(96 B), 1 acc += xyzz(192 B), 2 acc = 2 acc, 3 acc = 2 affine; acc is XYZZ (192 B). */
+int b200msm_test_fp_op(int curve, int op, const void *a, const void *b, void *r, uint64_t n);
+int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t n, int reps);
+
+/* ---- 1. Family A: sppark / organisers' harness ---------------------------------------------------------------- */
+typedef struct { int code; char *message; } RustError;   /* message is strdup'd; the Rust side frees it
+                                                            (P1A/6block/sppark/rust/src/lib.rs:17-24) */
+typedef struct { void *context; } MultiScalarMultContext; /* P1A/storswiftlabs/src/lib.rs:18-21 */
+
+RustError mult_pippenger_init(MultiScalarMultContext *context, const void *points_with_infinity, size_t npoints,
+                              size_t ffi_affine_sz);
+RustError mult_pippenger_inf(MultiScalarMultContext *context, uint64_t *out, const void *points_with_infinity,
+                             size_t npoints, size_t batch_size, const void *scalars, size_t ffi_affine_sz);
+/* not in the reference (its contexts leak): release a Family-A context */
+RustError mult_pippenger_free(MultiScalarMultContext *context);
+
+/* ---- 2. Family B: yrrid / combined-top-solutions -------------------------------------------------------------- */
+void *MSMAllocContext(int32_t maxPoints, int32_t maxBatches);
+int32_t MSMFreeContext(void *context);
+int32_t MSMPreprocessPoints(void *context, void *affinePointsPtr, uint32_t points);
+int32_t MSMRun(void *context, uint64_t *projectiveResultsPtr, void *scalarsPtr, uint32_t scalars);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
