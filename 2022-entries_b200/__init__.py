@@ -20,7 +20,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200msm.so")
 BLS12_377, BLS12_381 = 0, 1
 BASES_HARNESS, BASES_DISTINCT = 0, 1
-AFFINE_BYTES, SCALAR_BYTES, PROJECTIVE_BYTES, XYZZ_BYTES = 104, 32, 144, 192
+AFFINE_BYTES, SCALAR_BYTES, PROJECTIVE_BYTES = 104, 32, 144
+PARTIAL_BYTES = 224          # one GPU's partial result: XYZZ in the device representation (4 x 14 x 28-bit limbs)
+XYZZ_ABI_BYTES = 192         # test entry points: XYZZ as 4 arkworks field elements
 
 _lib = None
 
@@ -287,9 +289,9 @@ def test_fp_op(curve, op, a, b=None):
 
 
 def test_ec_op(curve, op, acc, other=None, reps=1):
-    acc = _as_u8(acc, XYZZ_BYTES, "acc").copy()
-    o = None if other is None else _as_u8(other, 96 if op != 1 else XYZZ_BYTES, "other")
-    rc = lib().b200msm_test_ec_op(curve, op, _ptr(acc), _ptr(o) if o is not None else None, acc.size // XYZZ_BYTES, reps)
+    acc = _as_u8(acc, XYZZ_ABI_BYTES, "acc").copy()
+    o = None if other is None else _as_u8(other, 96 if op != 1 else XYZZ_ABI_BYTES, "other")
+    rc = lib().b200msm_test_ec_op(curve, op, _ptr(acc), _ptr(o) if o is not None else None, acc.size // XYZZ_ABI_BYTES, reps)
     if rc != 0:
         raise MsmError(f"b200msm_test_ec_op: {rc}: {lib().b200msm_last_error(None).decode()}")
-    return acc.reshape(-1, XYZZ_BYTES)
+    return acc.reshape(-1, XYZZ_ABI_BYTES)

@@ -3,11 +3,12 @@
 //
 // Same coordinate system and formulas (EFD madd-2008-s, add-2008-s, dbl-2008-s-1, mdbl-2008-s-1) the reference
 // entries accumulate buckets in (sppark xyzz_t.hpp:97-249, matter-labs ec.cuh:418-598, yrrid Curve.cu:630-1127);
-// the code below is written from the formulas, with its own lazy-reduction bookkeeping:
+// the code below is written from the formulas, with its own lazy-reduction bookkeeping on top of fp.cuh:
 //
-//   BLS12-377 (Fp::subx<K> = a + K*p - b, no reduction): stored coordinates obey  X < 8p, Y < 4p, ZZ, ZZZ < 2p;
-//   every Montgomery multiply below has (bound a)*(bound b) <= 100 <= SLACK = 152 so its result is < 2p.
-//   BLS12-381 (C::TIGHT): every add/sub result is conditionally reduced below 2p, so all operands are < 2p.
+//   every field value is kept normalised (28-bit limbs) but only lazily reduced: stored coordinates obey
+//   X < 10p, Y < 5p, ZZ, ZZZ < 2p.  Fp::sub<K>(a, b) = a + K p - b needs value(b) < (K-1) p, and every multiply
+//   needs (bound a)(bound b) < 2^11 (BLS12-381; 2^15 on BLS12-377) for its result to be < 2p -- the largest product
+//   below is 13 * 13.  The per-line comments give the bound of each result in units of p.
 //
 // The exceptional cases of the group law are all handled (the harness replicates 2^15 distinct bases to 2^26, so
 // P+P and P+(-P) inside one bucket do occur): accumulator at infinity, equal points
@@ -23,8 +24,10 @@
 
 namespace b200msm {
 
-struct affine_t { fp x, y; };            // canonical (< p) Montgomery limbs; 96 bytes in the device tables
-struct xyzz_t { fp x, y, zz, zzz; };     // 192 bytes
+struct affine_t { fp x, y; };            // canonical (< p) Montgomery limbs; 112 bytes in the device tables
+struct xyzz_t { fp x, y, zz, zzz; };     // 224 bytes
+struct affine_abi_t { fp_abi x, y; };    // 96 bytes: arkworks (x, y), R = 2^384
+struct xyzz_abi_t { fp_abi x, y, zz, zzz; };
 
 template <class C> struct Ec {
     typedef Fp<C> F;
@@ -36,72 +39,72 @@ template <class C> struct Ec {
     FP_HD static void from_affine(xyzz_t &a, const fp &x, const fp &y) {
         a.x = x; a.y = y; F::set_one(a.zz); F::set_one(a.zzz);
     }
-    // 2 * (x, y) for an affine point (mdbl-2008-s-1, a = 0): 4M + 3S... here 3M + 3S + small
+    // 2 * (x, y) for an affine point (mdbl-2008-s-1, a = 0); x, y < 2p
     FP_HD static void dbl_affine(xyzz_t &r, const fp &x, const fp &y) {
         fp u, v, w, s, m, t;
-        F::addx(u, y, y);                 // U = 2Y            < 2p
-        F::sqr(v, u);                     // V = U^2
-        F::mul(w, u, v);                  // W = U*V
-        F::mul(s, x, v);                  // S = X*V
+        F::add(u, y, y);                  // U = 2Y                    4
+        F::sqr(v, u);                     // V = U^2                   2
+        F::mul(w, u, v);                  // W = U*V                   2
+        F::mul(s, x, v);                  // S = X*V                   2
         F::sqr(t, x);
-        F::addx(m, t, t);
-        F::addx(m, m, t);                 // M = 3X^2          < 6p
+        F::add(m, t, t);
+        F::add(m, m, t);                  // M = 3X^2                  6
         F::sqr(r.x, m);
-        F::addx(t, s, s);                 // 2S                < 4p
-        F::template subx<4>(r.x, r.x, t); // X3 = M^2 - 2S     < 6p
-        F::template subx<8>(t, s, r.x);   // S - X3            < 10p
-        F::mul(t, m, t);                  // 6 * 10 = 60
+        F::add(t, s, s);                  // 2S                        4
+        F::template sub<5>(r.x, r.x, t);  // X3 = M^2 - 2S             7
+        F::template sub<8>(t, s, r.x);    // S - X3                    10
+        F::mul(t, m, t);                  // 6 * 10
         F::mul(s, w, y);
-        F::template subx<2>(r.y, t, s);   // Y3                < 4p
+        F::template sub<3>(r.y, t, s);    // Y3                        5
         r.zz = v;
         r.zzz = w;
     }
     // a = 2a (dbl-2008-s-1, a = 0).  Infinity stays infinity (ZZ3 = V*0 = 0).
     FP_HD static void dbl(xyzz_t &a) {
         fp u, v, w, s, m, t;
-        F::addx(u, a.y, a.y);             // U = 2Y1           < 8p
-        F::sqr(v, u);                     // 64
-        F::mul(w, u, v);                  // 8 * 2
-        F::mul(s, a.x, v);                // 8 * 2
-        F::sqr(t, a.x);                   // 64
-        F::addx(m, t, t);
-        F::addx(m, m, t);                 // M = 3 X1^2        < 6p
+        F::add(u, a.y, a.y);              // U = 2Y1                   10
+        F::sqr(v, u);                     // 100
+        F::mul(w, u, v);                  // 10 * 2
+        F::mul(s, a.x, v);                // 10 * 2
+        F::sqr(t, a.x);                   // 100
+        F::add(m, t, t);
+        F::add(m, m, t);                  // M = 3 X1^2                6
         fp x3, y3;
         F::sqr(x3, m);                    // 36
-        F::addx(t, s, s);
-        F::template subx<4>(x3, x3, t);   // < 6p
-        F::template subx<8>(t, s, x3);    // < 10p
+        F::add(t, s, s);                  //                           4
+        F::template sub<5>(x3, x3, t);    // X3                        7
+        F::template sub<8>(t, s, x3);     // S - X3                    10
         F::mul(t, m, t);                  // 60
-        F::mul(y3, w, a.y);               // 2 * 4
-        F::template subx<2>(a.y, t, y3);  // < 4p
+        F::mul(y3, w, a.y);               // 2 * 5
+        F::template sub<3>(a.y, t, y3);   // Y3                        5
         a.x = x3;
         F::mul(a.zz, v, a.zz);
         F::mul(a.zzz, w, a.zzz);
     }
-    // acc += (x2, y2) with (x2, y2) affine, canonical, not infinity  (madd-2008-s: 8M + 2S)
+    // acc += (x2, y2) with (x2, y2) affine, < 2p, not infinity  (madd-2008-s: 8M + 2S)
     FP_HD static void madd(xyzz_t &acc, const fp &x2, const fp &y2) {
         if (is_inf(acc)) { from_affine(acc, x2, y2); return; }
         fp p, r, pp, ppp, q, t;
-        F::mul(p, x2, acc.zz);                  // U2                       < 2p
-        F::mul(r, y2, acc.zzz);                 // S2
-        F::template subx<8>(p, p, acc.x);       // P = U2 - X1              < 10p
-        F::template subx<4>(r, r, acc.y);       // R = S2 - Y1              < 6p
+        F::mul(p, x2, acc.zz);                  // U2                       2
+        F::mul(r, y2, acc.zzz);                 // S2                       2
+        F::template sub<11>(p, p, acc.x);       // P = U2 - X1              13
+        F::template sub<6>(r, r, acc.y);        // R = S2 - Y1              8
         if (F::is_zero(p)) {
             if (F::is_zero(r)) dbl_affine(acc, x2, y2); else set_inf(acc);
             return;
         }
-        F::sqr(pp, p);                          // 100
-        F::mul(ppp, p, pp);                     // 10 * 2
-        F::mul(q, acc.x, pp);                   // 8 * 2
-        F::sqr(t, r);                           // 36
-        F::template subx<2>(t, t, ppp);         // R^2 - PPP                < 4p
+        F::sqr(pp, p);                          // 13 * 13
+        F::mul(ppp, p, pp);                     // 13 * 2
+        F::mul(q, acc.x, pp);                   // 10 * 2
+        F::sqr(t, r);                           // 8 * 8
+        F::template sub<3>(t, t, ppp);          // R^2 - PPP                5
         fp q2;
-        F::addx(q2, q, q);                      // 2Q                       < 4p
-        F::template subx<4>(t, t, q2);          // X3                       < 8p
-        F::template subx<8>(q, q, t);           // Q - X3                   < 10p
-        F::mul(q, r, q);                        // 6 * 10
-        F::mul(r, acc.y, ppp);                  // 4 * 2
-        F::template subx<2>(acc.y, q, r);       // Y3                       < 4p
+        F::add(q2, q, q);                       // 2Q                       4
+        F::template sub<5>(t, t, q2);           // X3                       10
+        F::template sub<11>(q, q, t);           // Q - X3                   13
+        F::mul(q, r, q);                        // 8 * 13
+        F::mul(r, acc.y, ppp);                  // 5 * 2
+        F::template sub<3>(acc.y, q, r);        // Y3                       5
         acc.x = t;
         F::mul(acc.zz, acc.zz, pp);
         F::mul(acc.zzz, acc.zzz, ppp);
@@ -111,28 +114,28 @@ template <class C> struct Ec {
         if (is_inf(b)) return;
         if (is_inf(a)) { a = b; return; }
         fp u1, u2, s1, s2, pp, ppp, q, t;
-        F::mul(u1, a.x, b.zz);                  // 8 * 2
+        F::mul(u1, a.x, b.zz);                  // 10 * 2
         F::mul(u2, b.x, a.zz);
-        F::mul(s1, a.y, b.zzz);                 // 4 * 2
+        F::mul(s1, a.y, b.zzz);                 // 5 * 2
         F::mul(s2, b.y, a.zzz);
-        F::template subx<2>(u2, u2, u1);        // P                        < 4p
-        F::template subx<2>(s2, s2, s1);        // R                        < 4p
+        F::template sub<3>(u2, u2, u1);         // P                        5
+        F::template sub<3>(s2, s2, s1);         // R                        5
         if (F::is_zero(u2)) {
             if (F::is_zero(s2)) dbl(a); else set_inf(a);
             return;
         }
-        F::sqr(pp, u2);                         // 16
+        F::sqr(pp, u2);                         // 25
         F::mul(ppp, u2, pp);
         F::mul(q, u1, pp);
         F::sqr(t, s2);
-        F::template subx<2>(t, t, ppp);         // < 4p
+        F::template sub<3>(t, t, ppp);          //                          5
         fp q2;
-        F::addx(q2, q, q);                      // < 4p
-        F::template subx<4>(t, t, q2);          // X3 < 8p
-        F::template subx<8>(q, q, t);           // < 10p
-        F::mul(q, s2, q);                       // 4 * 10
+        F::add(q2, q, q);                       //                          4
+        F::template sub<5>(t, t, q2);           // X3                       10
+        F::template sub<11>(q, q, t);           // Q - X3                   13
+        F::mul(q, s2, q);                       // 5 * 13
         F::mul(s1, s1, ppp);
-        F::template subx<2>(a.y, q, s1);        // Y3 < 4p
+        F::template sub<3>(a.y, q, s1);         // Y3                       5
         a.x = t;
         F::mul(a.zz, a.zz, b.zz);
         F::mul(a.zz, a.zz, pp);
@@ -149,8 +152,8 @@ template <class C> struct Ec {
         F::mul(x, a.x, z2);
         F::mul(x, x, i2);
         F::mul(y, a.y, i);
-        F::reduce(x);
-        F::reduce(y);
+        F::csub_p(x);
+        F::csub_p(y);
     }
     // Non-inlined entry points for the cold kernels (bucket reduction, finalize, table build): one copy of each body
     // per curve instead of one per call site.
@@ -162,12 +165,14 @@ template <class C> struct Ec {
     EC_NI static void inv_ni(fp &r, const fp &a) {
         fp acc;
         F::set_one(acc);
-        for (int i = 383; i >= 0; i--) {
+        for (int i = FP_LIMBS * FP_BITS - 1; i >= 0; i--) {
             mul_ni(acc, acc, acc);
-            if ((F::pm2_limb(i >> 5) >> (i & 31)) & 1) mul_ni(acc, acc, a);
+            if ((F::pm2_limb(i / FP_BITS) >> (i % FP_BITS)) & 1) mul_ni(acc, acc, a);
         }
         r = acc;
     }
+    EC_NI static void from_abi_ni(fp &r, const fp_abi &a) { F::from_abi(r, a); }
+    EC_NI static void to_abi_ni(fp_abi &r, const fp &a) { F::to_abi(r, a); }
     EC_NI static void to_affine_ni(fp &x, fp &y, const xyzz_t &a) {
         fp i, i2, z2;
         inv_ni(i, a.zzz);
@@ -176,8 +181,8 @@ template <class C> struct Ec {
         mul_ni(x, a.x, z2);
         mul_ni(x, x, i2);
         mul_ni(y, a.y, i);
-        F::reduce(x);
-        F::reduce(y);
+        F::csub_p(x);
+        F::csub_p(y);
     }
 };
 

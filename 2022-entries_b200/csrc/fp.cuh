@@ -1,83 +1,74 @@
-// fp.cuh -- 384-bit Montgomery field arithmetic for sm_100a (12 x 32-bit limbs, lazily reduced).
+// fp.cuh -- base-field arithmetic for sm_100a: 14 limbs x 28 bits ("reduced radix"), Montgomery with R = 2^392.
 //
-// Replaces, for this path, the device field libraries of the reference entries
-// (yrrid MP.cu:141-367 + Curve.cu:21-449, matter-labs ff_dispatch_st.cuh:234-481, sppark
-// mont_t.cuh:39-58,353-427).  Written from scratch: one even/odd column Montgomery multiply whose
-// mad.lo.cc/madc.hi.cc pairs ptxas fuses into IMAD.WIDE.U32(.X) with a predicate carry (checked with
-// cuobjdump: 288 IMAD.WIDE per multiply), no final subtraction (the spare bits of the 384-bit
-// container absorb it), and subtraction as a + k*p - b with compile-time k*p immediates.
+// Why this representation (measured on B200, profiles/r01_imad_microbench.txt and
+// profiles/r01_ncu_accumulate_v1_carrychain.txt): integer multiplies issue only on the "fmaheavy" half of the FMA
+// pipe; plain IMAD.WIDE.U32 sustains 63 / clk / SM, but the carry-predicated IMAD.WIDE.U32.X that a 12 x 32-bit
+// multiplier is made of runs at exactly half that, and ptxas splits the constant-operand half of the reduction into
+// IMAD.X + IMAD.HI.U32.X pairs -- 576 heavy-pipe slots per multiply, pipe 89 % busy, issue slots 32 % busy.
+// With 28-bit limbs a column of 14 + 14 products (each < 2^60) fits a 64-bit accumulator, so the multiplier is
+// 14*14*2 - 14 = 378 plain IMAD.WIDE with NO carry flags; the little carry work left (one shift+add per round, one
+// normalisation at the end) goes to the ALU pipe, which was 11 % busy.  Stands in for yrrid MP.cu:141-367,
+// matter-labs ff_dispatch_st.cuh:234-481, sppark mont_t.cuh:353-427 (all 12 x 32-bit carry-chain multipliers).
 //
-// The same source compiles for the host (CARRY flag emulated) so tests/host_emul can check the limb
-// logic against the CPU oracle without a GPU.  The product never runs the host build.
+// Conventions
+//   value(a) = sum_i a.l[i] * 2^(28 i).  "Normalised": l[0..12] < 2^28 (l[13] holds whatever is left).
+//   Montgomery form x~ = x * 2^392 mod p.  The arkworks ABI uses 6 x u64 with R = 2^384; abi_to_fp / fp_to_abi convert
+//   (bit repack + one multiply by 2^400 resp. 2^384), once per base at table build and once per result.
+//   mul(a, b): limbs of a and b below 2^30 (normalised inputs, or sums of up to four normalised values), and
+//   value(a) * value(b) < 2^392 * p  (i.e. ka * kb < 2^15 for BLS12-377, 2^11 for BLS12-381 when a < ka p, b < kb p);
+//   result normalised, value < 2p.  The 11-15 spare bits make every bound in ec.cuh hold without value reductions.
+//   sub<K>(a, b) = a + K p - b limb-wise, K p stored "limb-dominant" (every limb >= 2^28 - 1) so no limb goes
+//   negative: requires b normalised and value(b) < (K - 1) p.  add/sub results are NOT normalised; norm() does it.
+//
+// The same source compiles for the host (plain C++), so tests/host_emul checks it against the CPU oracle without a
+// GPU.  The product never runs the host build.
 #pragma once
 #include <stdint.h>
 
 #if defined(__CUDACC__)
 #define FP_HD __host__ __device__ __forceinline__
-#define FP_D __device__ __forceinline__
 #else
 #define FP_HD inline
-#define FP_D inline
 #endif
 
 namespace b200msm {
 
-// ---------------------------------------------------------------------------------------------
-// carry-chain primitives
-#if defined(__CUDA_ARCH__)
-FP_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-FP_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-FP_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-FP_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-FP_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-FP_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
-FP_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-FP_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-FP_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-FP_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-#else
-// host emulation of the PTX condition-code register (tests only)
-static thread_local uint32_t g_cc = 0;
-inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
-inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + g_cc; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
-inline uint32_t addc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + g_cc; return (uint32_t)t; }
-inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; g_cc = (uint32_t)(t >> 32) & 1; return (uint32_t)t; }   // g_cc = borrow
-inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - g_cc; g_cc = (uint32_t)(t >> 32) & 1; return (uint32_t)t; }
-inline uint32_t subc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - g_cc; return (uint32_t)t; }
-inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
-inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c + g_cc; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
-inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + g_cc; g_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
-inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + g_cc; return (uint32_t)t; }
-#endif
+constexpr int FP_LIMBS = 14;
+constexpr int FP_BITS = 28;
+constexpr uint32_t FP_MASK = (1u << FP_BITS) - 1;
+
+struct fp { uint32_t l[FP_LIMBS]; };        // 56 bytes
+struct fp_abi { uint32_t w[12]; };          // arkworks Fq: 6 x u64 little-endian, Montgomery R = 2^384, canonical
 
 // ---------------------------------------------------------------------------------------------
-// curve parameters (cross-checked there against sppark bls12-377.hpp:10-39,
-// bls12-381.hpp:10-37, ff_config.cuh:13-40, SHM.cu:13-48).  Limb accessors are constexpr functions so
-// fully unrolled code sees immediates.
+// curve parameters in 28-bit limbs (SURVEY.md Appendix B values, re-sliced; tests/test_host_emul.py re-derives every
+// table below from p with Python integers).  constexpr accessors so unrolled code sees immediates.
 struct Bls12_377 {
     static constexpr int ID = 0;
     static constexpr int SCALAR_BITS = 253;
-    static constexpr uint32_t INV = 0xffffffffu;     // -p^-1 mod 2^32
-    static constexpr uint32_t P0INV = 0x00000001u;   //  p^-1 mod 2^32
-    static constexpr int SLACK = 152;                // floor(2^384 / p): mul(a<ka*p, b<kb*p) < 2p while ka*kb <= SLACK
-    static constexpr bool TIGHT = false;             // lazy bounds X<8p, Y<4p, ZZ,ZZZ<2p hold without extra reductions
-    static constexpr uint32_t B3 = 3;                // 3*b
+    static constexpr uint32_t INV = 0xfffffffu;      // -p^-1 mod 2^28
+    static constexpr uint32_t P0INV = 0x0000001u;    //  p^-1 mod 2^28
     FP_HD static constexpr uint32_t p(int i) {
-        constexpr uint32_t v[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu,
-                                    0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+        constexpr uint32_t v[14] = {0x0000001u, 0x08c0000u, 0x0000085u, 0x5d44300u, 0x800170bu, 0x2fba094u, 0xf1ef362u,
+                                    0x00f5138u, 0xa22d9f3u, 0xa1493b1u, 0xb05c06cu, 0x10eac63u, 0xa4617c5u, 0x0001ae3u};
         return v[i];
     }
-    FP_HD static constexpr uint32_t one(int i) {     // R mod p
-        constexpr uint32_t v[12] = {0xffffff68u, 0x02cdffffu, 0x7fffffb1u, 0x51409f83u, 0x8a7d3ff2u, 0x9f7db3a9u,
-                                    0x6e7c6305u, 0x7b4e97b7u, 0x803c84e8u, 0x4cf495bfu, 0xe2fdf49au, 0x008d6661u};
+    FP_HD static constexpr uint32_t one(int i) {     // 2^392 mod p
+        constexpr uint32_t v[14] = {0xfff67acu, 0x20fffffu, 0xfb0d727u, 0xe9203ffu, 0x249b0e4u, 0xe172345u, 0x955d771u,
+                                    0x2bf89aau, 0xb2833b2u, 0x98e116bu, 0x7dc5c97u, 0x0d43e93u, 0x2e3314bu, 0x00003b4u};
         return v[i];
     }
-    FP_HD static constexpr uint32_t r2(int i) {      // R^2 mod p
-        constexpr uint32_t v[12] = {0x9400cd22u, 0xb786686cu, 0xb00431b1u, 0x0329fcaau, 0x62d6b46du, 0x22a5f111u,
-                                    0x827dc3acu, 0xbfdf7d03u, 0x41790bf9u, 0x837e92f0u, 0x1e914b88u, 0x006dfccbu};
+    FP_HD static constexpr uint32_t cin(int i) {     // 2^400 mod p: mul(repack(x * 2^384), cin) = x * 2^392
+        constexpr uint32_t v[14] = {0xf67abddu, 0xcdbffffu, 0x0d714f0u, 0x5fed6fbu, 0x1adbe5bu, 0xebc50d7u, 0x49c2b74u,
+                                    0xd718fccu, 0x56fe5f2u, 0xd413a69u, 0xa9348beu, 0xf3d01dcu, 0xb9c0b1bu, 0x000070eu};
         return v[i];
     }
-    FP_HD static constexpr uint32_t r(int i) {       // scalar-field modulus
+    FP_HD static constexpr uint32_t cout(int i) {    // 2^384 mod p: mul(x * 2^392, cout) = x * 2^384
+        constexpr uint32_t v[14] = {0xfffff68u, 0xcdfffffu, 0xfffb102u, 0x9f837ffu, 0xff25140u, 0xa98a7d3u, 0x59f7db3u,
+                                    0x6e7c630u, 0xb4e97b7u, 0x3c84e87u, 0x495bf80u, 0xf49a4cfu, 0x661e2fdu, 0x00008d6u};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t r(int i) {       // scalar-field modulus, 8 x 32-bit
         constexpr uint32_t v[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
         return v[i];
     }
@@ -86,24 +77,26 @@ struct Bls12_377 {
 struct Bls12_381 {
     static constexpr int ID = 1;
     static constexpr int SCALAR_BITS = 255;
-    static constexpr uint32_t INV = 0xfffcfffdu;
-    static constexpr uint32_t P0INV = 0x00030003u;
-    static constexpr int SLACK = 9;
-    static constexpr bool TIGHT = true;              // only 3 spare bits: every add/sub result is brought back below 2p
-    static constexpr uint32_t B3 = 12;
+    static constexpr uint32_t INV = 0xffcfffdu;
+    static constexpr uint32_t P0INV = 0x0030003u;
     FP_HD static constexpr uint32_t p(int i) {
-        constexpr uint32_t v[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
-                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        constexpr uint32_t v[14] = {0xfffaaabu, 0xfefffffu, 0x3ffffb9u, 0xfffeb15u, 0x6241eabu, 0xa0f6b0fu, 0xf6730d2u,
+                                    0xf38512bu, 0x4774b84u, 0x4bacd76u, 0xba7b643u, 0xe69a4b1u, 0x1ea397fu, 0x001a011u};
         return v[i];
     }
     FP_HD static constexpr uint32_t one(int i) {
-        constexpr uint32_t v[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
-                                    0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        constexpr uint32_t v[14] = {0x347fcb8u, 0xd800000u, 0x002b119u, 0x0cde6d2u, 0xc7212e0u, 0x83a2090u, 0x037669fu,
+                                    0xda0f73eu, 0x9b09b42u, 0x1297bb0u, 0x515d98fu, 0x012ca7cu, 0x659fcfau, 0x000577au};
         return v[i];
     }
-    FP_HD static constexpr uint32_t r2(int i) {
-        constexpr uint32_t v[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
-                                    0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+    FP_HD static constexpr uint32_t cin(int i) {
+        constexpr uint32_t v[14] = {0x80e6299u, 0x3500034u, 0xeb12856u, 0xdeb2699u, 0xc988670u, 0x4ef6697u, 0x70983e8u,
+                                    0xa4e6fe9u, 0x3e8a053u, 0xecf271eu, 0xc20d323u, 0x6eb6385u, 0x47f1286u, 0x00156dau};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t cout(int i) {
+        constexpr uint32_t v[14] = {0x002fffdu, 0x0900000u, 0xc000276u, 0x000bc40u, 0x8baebf4u, 0x5753c75u, 0x55f4898u,
+                                    0x7052574u, 0x7ce5853u, 0x56ec6d7u, 0x71a97a2u, 0xe4935c0u, 0xec3fa80u, 0x0015f65u};
         return v[i];
     }
     FP_HD static constexpr uint32_t r(int i) {
@@ -112,22 +105,33 @@ struct Bls12_381 {
     }
 };
 
-// limb i of k*p, k small, as a compile-time constant
-template <class C> FP_HD constexpr uint32_t kp_limb(int k, int i) {
+// limb i of K*p in limb-dominant form: limbs 0..12 of K*p each borrow 2^28 from the limb above, so every limb is
+// >= 2^28 - 1 while the value is still exactly K*p.
+template <class C> FP_HD constexpr uint32_t kp_dom(int k, int i) {
     uint64_t carry = 0;
-    uint32_t out = 0;
+    uint32_t limb = 0;
     for (int j = 0; j <= i; j++) {
         uint64_t t = (uint64_t)C::p(j) * (uint32_t)k + carry;
-        out = (uint32_t)t;
-        carry = t >> 32;
+        limb = (uint32_t)(t & FP_MASK);
+        carry = t >> FP_BITS;
+        if (j == FP_LIMBS - 1) limb = (uint32_t)t;      // top limb keeps everything
     }
-    return out;
+    if (i < FP_LIMBS - 1) limb += (1u << FP_BITS);      // borrowed from above
+    if (i > 0) limb -= 1;                               // lent to below
+    return limb;
 }
 
-struct fp { uint32_t l[12]; };
+// Keeps a value opaque to the optimiser as a 32-bit register.  Without it NVVM widens the Montgomery factor m to
+// 64 bits (neg.s64 / and.b64) and every m * p_j becomes a 64 x 64 mul.lo.s64 -- one junk IADD3 per product in SASS.
+FP_HD uint32_t opaque32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    asm("" : "+r"(v));
+#endif
+    return v;
+}
 
 template <class C> struct Fp {
-    static constexpr int N = 12;
+    static constexpr int N = FP_LIMBS;
 
     FP_HD static void set_zero(fp &r) {
 #pragma unroll
@@ -143,164 +147,184 @@ template <class C> struct Fp {
         for (int i = 0; i < N; i++) o |= a.l[i];
         return o == 0;
     }
-
-    // r = a + b (no reduction; caller owns the bound)
+    // carry-propagate so limbs 0..12 are below 2^28 (limbs may be up to 2^32 - 1 on entry)
+    FP_HD static void norm(fp &a) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) {
+            uint32_t t = a.l[i] + c;
+            // a.l[i] + c cannot wrap: callers keep limbs below 2^31 and c < 2^4
+            a.l[i] = t & FP_MASK;
+            c = t >> FP_BITS;
+        }
+        a.l[N - 1] += c;
+    }
+    // r = a + b, normalised
     FP_HD static void add(fp &r, const fp &a, const fp &b) {
-        r.l[0] = add_cc(a.l[0], b.l[0]);
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
-        r.l[N - 1] = addc(a.l[N - 1], b.l[N - 1]);
+        for (int i = 0; i < N; i++) r.l[i] = a.l[i] + b.l[i];
+        norm(r);
     }
-    // r = a + K*p - b   (requires b <= K*p)
+    // r = a + K*p - b, normalised.  Requires b normalised, value(b) < (K-1) p, limbs of a below 2^30.
     template <int K> FP_HD static void sub(fp &r, const fp &a, const fp &b) {
-        fp t;
-        t.l[0] = add_cc(a.l[0], kp_limb<C>(K, 0));
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) t.l[i] = addc_cc(a.l[i], kp_limb<C>(K, i));
-        t.l[N - 1] = addc(a.l[N - 1], kp_limb<C>(K, N - 1));
-        r.l[0] = sub_cc(t.l[0], b.l[0]);
-#pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(t.l[i], b.l[i]);
-        r.l[N - 1] = subc(t.l[N - 1], b.l[N - 1]);
+        for (int i = 0; i < N; i++) r.l[i] = a.l[i] + kp_dom<C>(K, i) - b.l[i];
+        norm(r);
     }
-    // r = K*p - a  (requires a <= K*p)
+    // r = K*p - a (a normalised, value(a) < (K-1) p), normalised
     template <int K> FP_HD static void neg(fp &r, const fp &a) {
-        r.l[0] = sub_cc(kp_limb<C>(K, 0), a.l[0]);
 #pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = subc_cc(kp_limb<C>(K, i), a.l[i]);
-        r.l[N - 1] = subc(kp_limb<C>(K, N - 1), a.l[N - 1]);
+        for (int i = 0; i < N; i++) r.l[i] = kp_dom<C>(K, i) - a.l[i];
+        norm(r);
     }
-    // if (a >= K*p) a -= K*p
-    template <int K> FP_HD static void csub(fp &a) {
-        fp t;
-        t.l[0] = sub_cc(a.l[0], kp_limb<C>(K, 0));
+
+    // Montgomery product a*b / 2^392 mod p (normalised, value < 2p under the bounds in the header comment).
+    // Row i: t += a * b_i (14 IMAD.WIDE, no carries);  m = -t_0 / p mod 2^28;  t += m * p  (14 more; p_0 = 1 on BLS12-377
+    // costs nothing);  t_0 is now a multiple of 2^28: push t_0 >> 28 into t_1 and rename the columns down by one.
+    FP_HD static void mul(fp &r, const fp &a, const fp &b) {
+        uint64_t t[N];
 #pragma unroll
-        for (int i = 1; i < N; i++) t.l[i] = subc_cc(a.l[i], kp_limb<C>(K, i));
-        uint32_t borrow = subc(0, 0);   // 0xffffffff when a < K*p
+        for (int i = 0; i < N; i++) {
+            const uint32_t bi = b.l[i];
+            // the top column is fresh every round (written, not accumulated: no zero-initialised registers to add)
 #pragma unroll
-        for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : t.l[i];
+            for (int j = 0; j < N; j++) {
+                if (i == 0 || j == N - 1) t[j] = (uint64_t)a.l[j] * bi;
+                else t[j] += (uint64_t)a.l[j] * bi;
+            }
+            const uint32_t m = opaque32(((uint32_t)t[0] * C::INV) & FP_MASK);
+#pragma unroll
+            for (int j = 0; j < N; j++) t[j] += (uint64_t)m * C::p(j);
+            const uint64_t c = t[0] >> FP_BITS;
+#pragma unroll
+            for (int j = 0; j < N - 1; j++) t[j] = t[j + 1];
+            t[0] += c;
+        }
+        // columns 0..12 hold the result (column 13 of the last round was shifted into t[12])
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < N - 2; j++) {
+            uint64_t v = t[j] + c;
+            r.l[j] = (uint32_t)v & FP_MASK;
+            c = v >> FP_BITS;
+        }
+        {
+            uint64_t v = t[N - 2] + c;
+            r.l[N - 2] = (uint32_t)v & FP_MASK;
+            r.l[N - 1] = (uint32_t)(v >> FP_BITS);
+        }
     }
-    // canonical representative in [0, p) of a value below 16p
+    // a^2: the 91 cross products are taken once against the doubled operand (limbs of a below 2^29 here)
+    FP_HD static void sqr(fp &r, const fp &a) {
+        uint64_t t[2 * N];
+#pragma unroll
+        for (int j = 0; j < 2 * N; j++) t[j] = 0;
+        uint32_t a2[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) a2[j] = a.l[j] << 1;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            t[2 * i] += (uint64_t)a.l[i] * a.l[i];
+#pragma unroll
+            for (int j = i + 1; j < N; j++) t[i + j] += (uint64_t)a.l[i] * a2[j];
+        }
+        // Montgomery reduction of the 28 columns: column i is cleared, then its carry moves up
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t m = opaque32(((uint32_t)t[i] * C::INV) & FP_MASK);
+#pragma unroll
+            for (int j = 0; j < N; j++) t[i + j] += (uint64_t)m * C::p(j);
+            t[i + 1] += t[i] >> FP_BITS;
+        }
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < N - 1; j++) {
+            uint64_t v = t[N + j] + c;
+            r.l[j] = (uint32_t)v & FP_MASK;
+            c = v >> FP_BITS;
+        }
+        r.l[N - 1] = (uint32_t)(t[2 * N - 1] + c);
+    }
+
+    // canonical representative in [0, p): one multiply by the Montgomery one (value < 2p), then a conditional subtract
     FP_HD static void reduce(fp &a) {
-        if constexpr (!C::TIGHT) { csub<8>(a); csub<4>(a); }
-        csub<2>(a);
-        csub<1>(a);
+        fp one;
+        set_one(one);
+        fp t;
+        mul(t, a, one);
+        csub_p(t);
+        a = t;
     }
-    // a == 0 (mod p) for a < 16p.  A multiple k*p has low limb k*p0, so k = a0 * p0^-1 must be small: one
-    // multiply filters out all but ~2^-28 of the non-zero values before the exact comparison.
+    // a normalised, value < 2p:  if (a >= p) a -= p
+    FP_HD static void csub_p(fp &a) {
+        uint32_t d[N];
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t t = a.l[i] - C::p(i) - borrow;
+            borrow = t >> 31;
+            d[i] = (i < N - 1) ? (t & FP_MASK) : t;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) a.l[i] = borrow ? a.l[i] : d[i];
+    }
+    // a == 0 (mod p) for a lazily reduced a (value below 2^15 p).  A multiple k*p has low limb k*p_0, so
+    // k = a_0 / p_0 mod 2^28 must be small: one multiply filters all but 2^-12 of the non-zero values, the rest take
+    // the exact path.
     FP_HD static bool is_zero(const fp &a) {
-        uint32_t k = a.l[0] * C::P0INV;
-        if (k >= 16) return false;
+        uint32_t k = (a.l[0] * C::P0INV) & FP_MASK;
+        if (k >= (1u << 16)) return false;
         fp t = a;
+        norm(t);
         reduce(t);
         return is_literal_zero(t);
     }
 
-    // Montgomery product a*b/2^384 mod p, lazily reduced:  result < (ka*kb/SLACK + 1) * p for a < ka*p, b < kb*p,
-    // and a + p must stay below 2^384.
-    //
-    // Even/odd column form.  T = ev + od*2^32 with ev at limb positions 0..12 and od[j] at position j+1.  Round i
-    // adds a*b_i and m*p (m chosen so limb 0 cancels) with four 6-pair carry chains -- every pair is one
-    // IMAD.WIDE.U32.X -- then divides by 2^32 by renaming: od becomes the new ev, ev[2..] the new od, and the one
-    // limb that lands on an occupied position (ev[1] onto od[0]) is added with its carry parked in CC until the
-    // first madc of the next round.  T never exceeds a + p, so od needs no top carry limb.
-    FP_HD static void mul(fp &r, const fp &a, const fp &b) {
-        uint32_t ev[N + 1], od[N];
-#pragma unroll
-        for (int i = 0; i < N; i++) { ev[i] = 0; od[i] = 0; }
-        ev[N] = 0;
+    // arkworks ABI (6 x u64, R = 2^384, canonical) <-> internal (14 x 28, R = 2^392, canonical)
+    FP_HD static void repack_from_abi(fp &r, const fp_abi &a) {
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const uint32_t bi = b.l[i];
-            // od += (a1, a3, ...) * bi, taking in the carry parked by the previous round's merge
-            od[0] = (i == 0) ? mad_lo_cc(a.l[1], bi, od[0]) : madc_lo_cc(a.l[1], bi, od[0]);
-            od[1] = madc_hi_cc(a.l[1], bi, od[1]);
-#pragma unroll
-            for (int j = 2; j < N; j += 2) {
-                od[j] = madc_lo_cc(a.l[j + 1], bi, od[j]);
-                od[j + 1] = (j + 2 < N) ? madc_hi_cc(a.l[j + 1], bi, od[j + 1]) : madc_hi(a.l[j + 1], bi, od[j + 1]);
-            }
-            // ev += (a0, a2, ...) * bi
-            ev[0] = mad_lo_cc(a.l[0], bi, ev[0]);
-            ev[1] = madc_hi_cc(a.l[0], bi, ev[1]);
-#pragma unroll
-            for (int j = 2; j < N; j += 2) {
-                ev[j] = madc_lo_cc(a.l[j], bi, ev[j]);
-                ev[j + 1] = madc_hi_cc(a.l[j], bi, ev[j + 1]);
-            }
-            ev[N] = addc(ev[N], 0);
-            const uint32_t m = ev[0] * C::INV;
-            // ev += (p0, p2, ...) * m   -> ev[0] == 0
-            ev[0] = mad_lo_cc(C::p(0), m, ev[0]);
-            ev[1] = madc_hi_cc(C::p(0), m, ev[1]);
-#pragma unroll
-            for (int j = 2; j < N; j += 2) {
-                ev[j] = madc_lo_cc(C::p(j), m, ev[j]);
-                ev[j + 1] = madc_hi_cc(C::p(j), m, ev[j + 1]);
-            }
-            ev[N] = addc(ev[N], 0);
-            // od += (p1, p3, ...) * m
-            od[0] = mad_lo_cc(C::p(1), m, od[0]);
-            od[1] = madc_hi_cc(C::p(1), m, od[1]);
-#pragma unroll
-            for (int j = 2; j < N; j += 2) {
-                od[j] = madc_lo_cc(C::p(j + 1), m, od[j]);
-                od[j + 1] = (j + 2 < N) ? madc_hi_cc(C::p(j + 1), m, od[j + 1]) : madc_hi(C::p(j + 1), m, od[j + 1]);
-            }
-            // divide by 2^32: new ev = od (+ ev[1] on limb 0, carry parked), new od = ev >> 64
-            const uint32_t e0 = add_cc(od[0], ev[1]);
-            uint32_t nod[N];
-#pragma unroll
-            for (int j = 0; j < N - 1; j++) nod[j] = ev[j + 2];
-            nod[N - 1] = 0;
-            ev[0] = e0;
-#pragma unroll
-            for (int j = 1; j < N; j++) ev[j] = od[j];
-            ev[N] = 0;
-#pragma unroll
-            for (int j = 0; j < N; j++) od[j] = nod[j];
+            const int bit = FP_BITS * i, w = bit >> 5, s = bit & 31;
+            uint64_t v = a.w[w];
+            if (w + 1 < 12) v |= (uint64_t)a.w[w + 1] << 32;
+            r.l[i] = (uint32_t)(v >> s) & FP_MASK;
         }
-        // r = ev + od*2^32, consuming the parked carry
-        r.l[0] = ev[0];
-#pragma unroll
-        for (int j = 1; j < N - 1; j++) r.l[j] = addc_cc(ev[j], od[j - 1]);
-        r.l[N - 1] = addc(ev[N - 1], od[N - 2]);
     }
-    FP_HD static void sqr(fp &r, const fp &a) { mul(r, a, a); }
+    FP_HD static void repack_to_abi(fp_abi &r, const fp &a) {
+#pragma unroll
+        for (int w = 0; w < 12; w++) {
+            // bits [32w, 32w+32) come from at most three 28-bit limbs
+            const int bit = 32 * w, i = bit / FP_BITS, s = bit % FP_BITS;
+            uint64_t v = (uint64_t)a.l[i] >> s;
+            if (i + 1 < N) v |= (uint64_t)a.l[i + 1] << (FP_BITS - s);
+            if (i + 2 < N && 2 * FP_BITS - s < 32) v |= (uint64_t)a.l[i + 2] << (2 * FP_BITS - s);
+            r.w[w] = (uint32_t)v;
+        }
+    }
+    FP_HD static void from_abi(fp &r, const fp_abi &a) {
+        fp t, c;
+        repack_from_abi(t, a);
+#pragma unroll
+        for (int i = 0; i < N; i++) c.l[i] = C::cin(i);
+        mul(r, t, c);
+        csub_p(r);
+    }
+    FP_HD static void to_abi(fp_abi &r, const fp &a) {
+        fp t = a, c;
+        norm(t);
+#pragma unroll
+        for (int i = 0; i < N; i++) c.l[i] = C::cout(i);
+        mul(t, t, c);
+        csub_p(t);
+        repack_to_abi(r, t);
+    }
 
-    // Montgomery form <-> canonical integer
-    FP_HD static void to_mont(fp &r, const fp &a) {
-        fp t;
-#pragma unroll
-        for (int i = 0; i < N; i++) t.l[i] = C::r2(i);
-        mul(r, a, t);
-        reduce(r);
-    }
-    FP_HD static void from_mont(fp &r, const fp &a) {
-        fp t;
-        set_zero(t);
-        t.l[0] = 1;
-        mul(r, a, t);
-        reduce(r);
-    }
-    // a^(p-2): 1/a for a != 0 (mod p); input below 2p, output below 2p.  Fixed square-and-multiply ladder.
-    FP_HD static void inv(fp &r, const fp &a) {
-        fp acc;
-        set_one(acc);
-        // exponent p - 2, scanned from the top bit
-        for (int i = 383; i >= 0; i--) {
-            sqr(acc, acc);
-            uint32_t w = (i >> 5);
-            uint32_t e = pm2_limb(w);
-            if ((e >> (i & 31)) & 1) mul(acc, acc, a);
-        }
-        r = acc;
-    }
-    FP_HD static constexpr uint32_t pm2_const(int i) {   // limb i of p - 2
+    // limb i of p - 2 (exponent of the Fermat inversion), 28-bit limbs
+    FP_HD static constexpr uint32_t pm2_const(int i) {
         uint32_t borrow = 2, out = 0;
         for (int j = 0; j <= i; j++) {
             uint32_t pj = C::p(j);
-            out = pj - borrow;
+            out = (pj - borrow) & FP_MASK;
             borrow = (pj < borrow) ? 1u : 0u;
         }
         return out;
@@ -312,14 +336,15 @@ template <class C> struct Fp {
             if ((uint32_t)i == w) v = pm2_const(i);
         return v;
     }
-    // lazy/tight policy helpers: in lazy mode (BLS12-377) r = a + KL*p - b, bound a + KL*p; in tight mode
-    // (BLS12-381) operands are below 2p and the result is brought back below 2p.
-    template <int KL> FP_HD static void subx(fp &r, const fp &a, const fp &b) {
-        if constexpr (C::TIGHT) { sub<2>(r, a, b); csub<2>(r); } else { sub<KL>(r, a, b); }
-    }
-    FP_HD static void addx(fp &r, const fp &a, const fp &b) {
-        add(r, a, b);
-        if constexpr (C::TIGHT) csub<2>(r);
+    // a^(p-2) = 1/a (a normalised, value < 2p; result normalised, < 2p)
+    FP_HD static void inv(fp &r, const fp &a) {
+        fp acc;
+        set_one(acc);
+        for (int i = N * FP_BITS - 1; i >= 0; i--) {
+            mul(acc, acc, acc);
+            if ((pm2_limb(i / FP_BITS) >> (i % FP_BITS)) & 1) mul(acc, acc, a);
+        }
+        r = acc;
     }
 };
 

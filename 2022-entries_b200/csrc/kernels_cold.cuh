@@ -14,20 +14,30 @@ namespace b200msm {
 // ---------------------------------------------------------------------------------------------
 // a9: bucket reduction.  For a window with buckets B_0..B_{n-1} (bucket k carries weight k+1) the window sum is
 //   sum_k B_k + W0(B),  W0(B) = sum_k k*B_k = sum_t T_t + m * W0(S),   S_t = sum_j B_{tm+j},  T_t = sum_j j*B_{tm+j}.
-// One thread produces (S_t, T_t) for m consecutive inputs with the running-sum trick (2 adds per input); the host
-// applies the kernel level by level until 32 or fewer elements are left (k_finalize).  INDIRECT reads level 0
-// through the piece table (a bucket is the sum of its pieces, almost always exactly one).  SUM_ONLY skips T.
-template <class C, bool INDIRECT, bool SUM_ONLY>
-__global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const uint32_t *__restrict__ piece_off, uint32_t n_out, uint32_t m,
+// One thread produces (S_t, T_t) for m consecutive inputs with the running-sum trick (2 adds per input); S_t is
+// stored, the T_t of a block are tree-summed in shared memory (only their plain sum is ever needed) and stored once
+// per block.  The host applies the kernel level by level (m = 8: every level but the first is latency-bound, so
+// short serial chains and many threads) until 32 or fewer S are left for k_finalize.  INDIRECT reads level 0 through
+// the piece table (a bucket is the sum of its pieces, almost always exactly one).
+template <class C> __device__ __forceinline__ void block_tree_sum(xyzz_t &v, xyzz_t *sh) {
+    for (uint32_t o = blockDim.x >> 1; o > 0; o >>= 1) {
+        __syncthreads();
+        if (threadIdx.x >= o && threadIdx.x < 2 * o) store_xyzz(sh + threadIdx.x - o, v);
+        __syncthreads();
+        if (threadIdx.x < o) { xyzz_t t; load_xyzz(t, sh + threadIdx.x); Ec<C>::add_ni(v, t); }
+    }
+}
+template <class C, bool INDIRECT>
+__global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const uint32_t *__restrict__ piece_off, uint32_t m,
                                                        xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out) return;
+    __shared__ xyzz_t sh[64];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the outputs exactly
     xyzz_t run, tot, b;
     Ec<C>::set_inf(run);
     Ec<C>::set_inf(tot);
     for (uint32_t jj = m; jj-- > 0;) {
         uint32_t k = t * m + jj;
-        if (!SUM_ONLY && jj + 1 < m) Ec<C>::add_ni(tot, run);      // after the loop: tot = sum_j j * B_j
+        if (jj + 1 < m) Ec<C>::add_ni(tot, run);                   // after the loop: tot = sum_j j * B_j
         if (INDIRECT) {
             uint32_t p0 = piece_off[k], p1 = piece_off[k + 1];
             for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, in + q); Ec<C>::add_ni(run, b); }
@@ -37,15 +47,28 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
         }
     }
     store_xyzz(outS + t, run);
-    if (!SUM_ONLY) store_xyzz(outT + t, tot);
+    block_tree_sum<C>(tot, sh);
+    if (threadIdx.x == 0) store_xyzz(outT + blockIdx.x, tot);
+}
+// out[g] = sum of in[g*group .. (g+1)*group)   (one block per group)
+template <class C>
+__global__ void __launch_bounds__(128) k_block_sum(const xyzz_t *__restrict__ in, uint32_t group, xyzz_t *__restrict__ out) {
+    __shared__ xyzz_t sh[64];
+    xyzz_t v, b;
+    Ec<C>::set_inf(v);
+    for (uint32_t k = threadIdx.x; k < group; k += blockDim.x) { load_xyzz(b, in + (size_t)blockIdx.x * group + k); Ec<C>::add_ni(v, b); }
+    block_tree_sum<C>(v, sh);
+    if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, v);
 }
 
 // ---------------------------------------------------------------------------------------------
-// a10: finalize (one warp).  Per folded window f the host hands a list of terms, each an array of <= 32 points:
-//   kind 0: 2^shift * sum(arr)        kind 1: 2^shift * sum_k k * arr[k]
+// a10: finalize (one block, one warp per term).  Per folded window f the host hands a list of terms, each an array of
+// <= 32 points:   kind 0: 2^shift * sum(arr)        kind 1: 2^shift * sum_k k * arr[k]
 // window value = sum of its terms; result = Horner over windows with c doublings; then either the XYZZ value is
-// stored (partial result of one GPU) or it is normalised to the caller's Jacobian (x, y, z = 1) / (1, 1, 0).
-
+// stored (partial result of one GPU) or it is exported as an arkworks G1Projective: Jacobian (X*ZZ, Y*ZZZ, ZZ) -- with
+// ZZ = z^2, ZZZ = z^3 that is (x z^4, y z^6, z^2), a representative of (x, y) that needs no inversion (the harness
+// compares projectively / normalises on its side) -- or (1, 1, 0) for infinity.  All limbs canonical (< p).
+#define FIN_WARPS 8
 template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
     // tree sum of the 32 lanes' points through shared memory; result in lane 0
     const int lane = threadIdx.x & 31;
@@ -58,15 +81,16 @@ template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
     __syncwarp();
 }
 template <class C>
-__global__ void __launch_bounds__(32) k_finalize(fin_args_t a, xyzz_t *__restrict__ out_xyzz, uint32_t *__restrict__ out_jac, int extra_n, const xyzz_t *__restrict__ extra) {
-    __shared__ xyzz_t sh[16];
-    const int lane = threadIdx.x;
-    xyzz_t total;
+__global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_t *__restrict__ out_xyzz, uint32_t *__restrict__ out_jac, int extra_n, const xyzz_t *__restrict__ extra) {
+    __shared__ xyzz_t sh[FIN_WARPS][16];
+    __shared__ xyzz_t slot[FIN_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    xyzz_t total;                       // meaningful in thread 0
     Ec<C>::set_inf(total);
     for (int f = a.F - 1; f >= 0; f--) {
-        xyzz_t win;
-        Ec<C>::set_inf(win);
-        for (int ti = 0; ti < a.nterms; ti++) {
+        xyzz_t part;                    // this warp's share of the window value (lane 0)
+        Ec<C>::set_inf(part);
+        for (int ti = warp; ti < a.nterms; ti += FIN_WARPS) {
             const fin_term_t &tm = a.term[ti];
             xyzz_t v;
             Ec<C>::set_inf(v);
@@ -79,43 +103,90 @@ __global__ void __launch_bounds__(32) k_finalize(fin_args_t a, xyzz_t *__restric
                     v = r;
                 }
             }
-            warp_sum<C>(v, sh);
+            warp_sum<C>(v, sh[warp]);
             if (lane == 0) {
                 for (uint32_t s = 0; s < tm.shift; s++) Ec<C>::dbl_ni(v);
-                Ec<C>::add_ni(win, v);
+                Ec<C>::add_ni(part, v);
             }
         }
-        if (lane == 0) {
-            if (f != a.F - 1) for (int s = 0; s < a.c; s++) Ec<C>::dbl_ni(total);
-            Ec<C>::add_ni(total, win);
+        if (lane == 0) store_xyzz(&slot[warp], part);
+        __syncthreads();
+        if (warp == 0) {
+            xyzz_t v;
+            Ec<C>::set_inf(v);
+            if (lane < FIN_WARPS) load_xyzz(v, &slot[lane]);
+            warp_sum<C>(v, sh[0]);
+            if (lane == 0) {
+                if (f != a.F - 1) for (int s = 0; s < a.c; s++) Ec<C>::dbl_ni(total);
+                Ec<C>::add_ni(total, v);
+            }
         }
+        __syncthreads();
     }
+    if (warp != 0) return;
     // optional: add further partial results (other GPUs' XYZZ partials, lane-parallel)
     if (extra_n > 0) {
         xyzz_t v;
         Ec<C>::set_inf(v);
         for (int k = lane; k < extra_n; k += 32) { xyzz_t t; load_xyzz(t, extra + k); Ec<C>::add_ni(v, t); }
-        warp_sum<C>(v, sh);
+        warp_sum<C>(v, sh[0]);
         if (lane == 0) Ec<C>::add_ni(total, v);
     }
     if (lane == 0) {
         if (out_xyzz) {
-            Fp<C>::reduce(total.x); Fp<C>::reduce(total.y); Fp<C>::reduce(total.zz); Fp<C>::reduce(total.zzz);
             store_xyzz(out_xyzz, total);
         }
         if (out_jac) {
-            // arkworks G1Projective (Jacobian x, y, z; 3 x 48 bytes): finite -> (x_aff, y_aff, 1); infinity -> (1, 1, 0)
             fp x, y, z;
             if (Ec<C>::is_inf(total)) { Fp<C>::set_one(x); Fp<C>::set_one(y); Fp<C>::set_zero(z); }
-            else { Ec<C>::to_affine_ni(x, y, total); Fp<C>::set_one(z); }
+            else {
+                Ec<C>::mul_ni(x, total.x, total.zz);
+                Ec<C>::mul_ni(y, total.y, total.zzz);
+                z = total.zz;
+            }
+            fp_abi ox, oy, oz;
+            Ec<C>::to_abi_ni(ox, x); Ec<C>::to_abi_ni(oy, y); Ec<C>::to_abi_ni(oz, z);
 #pragma unroll
-            for (int i = 0; i < 12; i++) { out_jac[i] = x.l[i]; out_jac[12 + i] = y.l[i]; out_jac[24 + i] = z.l[i]; }
+            for (int i = 0; i < 12; i++) { out_jac[i] = ox.w[i]; out_jac[12 + i] = oy.w[i]; out_jac[24 + i] = oz.w[i]; }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // a11: base tables.
+// arkworks G1Affine records (x, y: 6 x u64 Montgomery R = 2^384; infinity flag at byte 96; stride bytes) -> table 0 in
+// the device representation (14 x 28-bit limbs, R = 2^392) + infinity bitmask
+template <class C>
+__global__ void __launch_bounds__(128) k_convert_points(const uint8_t *__restrict__ src, uint32_t n, uint32_t stride, affine_t *__restrict__ table0, uint32_t *__restrict__ infmask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool inf = false;
+    if (i < n) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(src + (size_t)i * stride);   // 104 and 96 are multiples of 8
+        fp_abi ax, ay;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { ax.w[k] = p[k]; ay.w[k] = p[12 + k]; }
+        affine_t o;
+        Ec<C>::from_abi_ni(o.x, ax);
+        Ec<C>::from_abi_ni(o.y, ay);
+        store_affine(table0 + i, o);
+        inf = stride > 96 && src[(size_t)i * stride + 96] != 0;
+    }
+    uint32_t bits = __ballot_sync(0xffffffffu, inf);
+    if ((threadIdx.x & 31) == 0 && i < n) infmask[i >> 5] = bits;
+}
+// table 0 back as arkworks (x, y) records of 96 bytes (tests)
+template <class C>
+__global__ void __launch_bounds__(128) k_export_points(const affine_t *__restrict__ table0, uint32_t n, uint32_t *__restrict__ dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t a;
+    load_affine(a, table0 + i);
+    fp_abi ox, oy;
+    Ec<C>::to_abi_ni(ox, a.x);
+    Ec<C>::to_abi_ni(oy, a.y);
+#pragma unroll
+    for (int k = 0; k < 12; k++) { dst[(size_t)i * 24 + k] = ox.w[k]; dst[(size_t)i * 24 + 12 + k] = oy.w[k]; }
+}
 // tmp[i] = 2^k * src[i]  (XYZZ, not normalised)
 template <class C>
 __global__ void __launch_bounds__(128) k_double_n(const affine_t *__restrict__ src, uint32_t n, int k, xyzz_t *__restrict__ tmp) {
@@ -143,9 +214,10 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restric
     F::set_one(acc);
     for (uint32_t k = 0; k < cnt; k++) {
         fp z;
-        const uint4 *s = reinterpret_cast<const uint4 *>(&tmp[base + k].zzz);
-        uint4 *d = reinterpret_cast<uint4 *>(&z);
-        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+        const uint2 *s = reinterpret_cast<const uint2 *>(&tmp[base + k].zzz);     // 56-byte field: 8-byte aligned
+        uint2 *d = reinterpret_cast<uint2 *>(&z);
+#pragma unroll
+        for (int v = 0; v < 7; v++) d[v] = s[v];
         if (F::is_zero(z)) F::set_one(z);
         prefix[k] = acc;
         Ec<C>::mul_ni(acc, acc, z);
@@ -166,8 +238,8 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restric
         Ec<C>::mul_ni(o.x, q.x, z2);
         Ec<C>::mul_ni(o.x, o.x, i2);
         Ec<C>::mul_ni(o.y, q.y, i1);
-        F::reduce(o.x);
-        F::reduce(o.y);
+        F::csub_p(o.x);
+        F::csub_p(o.y);
         store_affine(dst + base + k, o);
     }
 }
@@ -213,41 +285,46 @@ __global__ void __launch_bounds__(256) k_gen_scalars(uint32_t n, uint64_t seed, 
     o[0] = make_uint4(s[0], s[1], s[2], s[3]);
     o[1] = make_uint4(s[4], s[5], s[6], s[7]);
 }
-// test entry points: element-wise field / curve operations on device arrays
+// test entry points: element-wise field / curve operations.  Operands and results are arkworks-ABI field elements
+// (48 bytes, R = 2^384, canonical); XYZZ records are 4 such elements (192 bytes), affine 2 (96 bytes).
 template <class C>
-__global__ void k_test_fp(int op, const fp *a, const fp *b, fp *r, uint32_t n) {
+__global__ void k_test_fp(int op, const fp_abi *a, const fp_abi *b, fp_abi *r, uint32_t n) {
     typedef Fp<C> F;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp x = a[i], y = b[i], t;
+    fp x, y, t;
+    Ec<C>::from_abi_ni(x, a[i]);
+    Ec<C>::from_abi_ni(y, b[i]);
     switch (op) {
     case 0: F::mul(t, x, y); break;
     case 1: F::add(t, x, y); break;
     case 2: F::template sub<2>(t, x, y); break;
     case 3: F::sqr(t, x); break;
     case 4: Ec<C>::inv_ni(t, x); break;
-    case 5: F::to_mont(t, x); break;
-    case 6: F::from_mont(t, x); break;
-    default: t = x;
+    default: t = x;                       // 5: ABI round trip
     }
-    F::reduce(t);
-    r[i] = t;
+    Ec<C>::to_abi_ni(r[i], t);
 }
 template <class C>
-__global__ void k_test_ec(int op, xyzz_t *acc, const void *other, uint32_t n, int reps) {
+__global__ void k_test_ec(int op, xyzz_abi_t *acc, const void *other, uint32_t n, int reps) {
     typedef Ec<C> E;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    xyzz_t q;
-    load_xyzz(q, acc + i);
-    for (int k = 0; k < reps; k++) {
-        if (op == 0) { affine_t a; load_affine(a, (const affine_t *)other + i); E::madd(q, a.x, a.y); }
-        else if (op == 1) { xyzz_t o; load_xyzz(o, (const xyzz_t *)other + i); E::add_ni(q, o); }
-        else if (op == 2) E::dbl_ni(q);
-        else if (op == 3) { affine_t a; load_affine(a, (const affine_t *)other + i); E::dbl_affine_ni(q, a.x, a.y); }
+    xyzz_t q, o;
+    affine_t a;
+    E::from_abi_ni(q.x, acc[i].x); E::from_abi_ni(q.y, acc[i].y); E::from_abi_ni(q.zz, acc[i].zz); E::from_abi_ni(q.zzz, acc[i].zzz);
+    if (op == 0 || op == 3) { E::from_abi_ni(a.x, ((const affine_abi_t *)other)[i].x); E::from_abi_ni(a.y, ((const affine_abi_t *)other)[i].y); }
+    if (op == 1) {
+        const xyzz_abi_t &s = ((const xyzz_abi_t *)other)[i];
+        E::from_abi_ni(o.x, s.x); E::from_abi_ni(o.y, s.y); E::from_abi_ni(o.zz, s.zz); E::from_abi_ni(o.zzz, s.zzz);
     }
-    Fp<C>::reduce(q.x); Fp<C>::reduce(q.y); Fp<C>::reduce(q.zz); Fp<C>::reduce(q.zzz);
-    store_xyzz(acc + i, q);
+    for (int k = 0; k < reps; k++) {
+        if (op == 0) E::madd(q, a.x, a.y);          // the inlined form the accumulate kernel uses
+        else if (op == 1) E::add_ni(q, o);
+        else if (op == 2) E::dbl_ni(q);
+        else if (op == 3) E::dbl_affine_ni(q, a.x, a.y);
+    }
+    E::to_abi_ni(acc[i].x, q.x); E::to_abi_ni(acc[i].y, q.y); E::to_abi_ni(acc[i].zz, q.zz); E::to_abi_ni(acc[i].zzz, q.zzz);
 }
 
 }  // namespace b200msm

@@ -1,7 +1,7 @@
 // kernels_common.cuh -- curve-independent kernels (included by msm.cu only):
 //   k_scan_*         a5  exclusive prefix sums (bucket offsets, piece offsets)
 //   k_piece_*        a5  split buckets into pieces of at most Lmax points, order pieces by decreasing length
-//   k_convert_points a11 arkworks G1Affine records -> base table 0 + infinity bitmask;  k_replicate: test bases
+//   k_replicate      a11 test bases: copy the first entries of table 0 up to n
 #pragma once
 #include "kernels_util.cuh"
 
@@ -154,26 +154,12 @@ __global__ void __launch_bounds__(PIECE_TPB) k_piece_order(const uint32_t *__res
 
 // ---------------------------------------------------------------------------------------------
 // a11 (curve-independent part)
-// arkworks G1Affine (x, y: 6 x u64 Montgomery; infinity flag at byte 96; stride bytes) -> table 0 + infinity bitmask
-__global__ void __launch_bounds__(256) k_convert_points(const uint8_t *__restrict__ src, uint32_t n, uint32_t stride, affine_t *__restrict__ table0, uint32_t *__restrict__ infmask) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool inf = false;
-    if (i < n) {
-        const uint64_t *p = reinterpret_cast<const uint64_t *>(src + (size_t)i * stride);   // 104 and 96 are both multiples of 8
-        uint64_t *d = reinterpret_cast<uint64_t *>(table0 + i);
-#pragma unroll
-        for (int k = 0; k < 12; k++) d[k] = p[k];
-        inf = stride > 96 && src[(size_t)i * stride + 96] != 0;
-    }
-    uint32_t bits = __ballot_sync(0xffffffffu, inf);
-    if ((threadIdx.x & 31) == 0 && i < n) infmask[i >> 5] = bits;
-}
 // replicate the first `have` entries of a table up to n (vector doubling, as the reference generator does)
 __global__ void __launch_bounds__(256) k_replicate(affine_t *table, uint32_t have, uint32_t n) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one uint4 per thread
-    size_t total = (size_t)(n - have) * 6;
+    size_t total = (size_t)(n - have) * AFF_VEC;
     if (idx >= total) return;
-    size_t e = have + idx / 6, k = idx % 6;
+    size_t e = have + idx / AFF_VEC, k = idx % AFF_VEC;
     reinterpret_cast<uint4 *>(table + e)[k] = reinterpret_cast<const uint4 *>(table + (e % have))[k];
 }
 

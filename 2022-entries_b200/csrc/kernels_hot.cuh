@@ -26,10 +26,13 @@ template <class C> struct ScalarOps {
 #pragma unroll
         for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)C::r(i) * K + carry; kr[i] = (uint32_t)t; carry = t >> 32; }
         uint32_t t[8];
-        t[0] = sub_cc(s[0], kr[0]);
+        uint32_t borrow = 0;
 #pragma unroll
-        for (int i = 1; i < 8; i++) t[i] = subc_cc(s[i], kr[i]);
-        uint32_t borrow = subc(0, 0);
+        for (int i = 0; i < 8; i++) {
+            uint64_t d = (uint64_t)s[i] - kr[i] - borrow;
+            t[i] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) s[i] = borrow ? s[i] : t[i];
     }
@@ -42,9 +45,13 @@ template <class C> struct ScalarOps {
     __device__ static bool fold_top_bit(uint32_t (&s)[8]) {
         const int tb = C::SCALAR_BITS - 1;
         if (!((s[tb >> 5] >> (tb & 31)) & 1)) return false;
-        s[0] = sub_cc(C::r(0), s[0]);
+        uint32_t borrow = 0;
 #pragma unroll
-        for (int i = 1; i < 8; i++) s[i] = subc_cc(C::r(i), s[i]);
+        for (int i = 0; i < 8; i++) {
+            uint64_t d = (uint64_t)C::r(i) - s[i] - borrow;
+            s[i] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
         return true;
     }
 };
@@ -97,7 +104,7 @@ __global__ void __launch_bounds__(ACC_TPB) k_accumulate(const affine_t *__restri
                                                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
                                                         const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
                                                         xyzz_t *__restrict__ res) {
-    __shared__ uint4 stage[2][6][ACC_TPB];
+    __shared__ uint4 stage[2][AFF_VEC][ACC_TPB];
     uint32_t j = blockIdx.x * ACC_TPB + threadIdx.x;
     if (j >= *npieces_ptr) return;
     const uint32_t piece = order[j];
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(ACC_TPB) k_accumulate(const affine_t *__restri
         ref = __ldg(refs + start);
         const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref & 0x7fffffffu));
 #pragma unroll
-        for (int k = 0; k < 6; k++) cp_async16(&stage[0][k][threadIdx.x], src + k);
+        for (int k = 0; k < AFF_VEC; k++) cp_async16(&stage[0][k][threadIdx.x], src + k);
     }
     cp_async_commit();
     for (uint32_t i = 0; i < len; i++) {
@@ -117,15 +124,15 @@ __global__ void __launch_bounds__(ACC_TPB) k_accumulate(const affine_t *__restri
             ref_next = __ldg(refs + start + i + 1);
             const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref_next & 0x7fffffffu));
 #pragma unroll
-            for (int k = 0; k < 6; k++) cp_async16(&stage[(i + 1) & 1][k][threadIdx.x], src + k);
+            for (int k = 0; k < AFF_VEC; k++) cp_async16(&stage[(i + 1) & 1][k][threadIdx.x], src + k);
         }
         cp_async_commit();
         cp_async_wait<1>();
         affine_t pt;
         uint4 *t = reinterpret_cast<uint4 *>(&pt);
 #pragma unroll
-        for (int k = 0; k < 6; k++) t[k] = stage[i & 1][k][threadIdx.x];
-        if (ref >> 31) Fp<C>::template neg<1>(pt.y, pt.y);
+        for (int k = 0; k < AFF_VEC; k++) t[k] = stage[i & 1][k][threadIdx.x];
+        if (ref >> 31) Fp<C>::template neg<2>(pt.y, pt.y);
         Ec<C>::madd(acc, pt.x, pt.y);
         ref = ref_next;
     }

@@ -14,29 +14,33 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+constexpr int AFF_VEC = sizeof(affine_t) / 16;     // 7 x 16 bytes
+constexpr int XYZZ_VEC = sizeof(xyzz_t) / 16;      // 14 x 16 bytes
+static_assert(sizeof(affine_t) == 112 && sizeof(xyzz_t) == 224, "device record sizes");
+
 __device__ __forceinline__ void load_xyzz(xyzz_t &d, const xyzz_t *src) {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
     uint4 *t = reinterpret_cast<uint4 *>(&d);
 #pragma unroll
-    for (int i = 0; i < 12; i++) t[i] = s[i];
+    for (int i = 0; i < XYZZ_VEC; i++) t[i] = s[i];
 }
 __device__ __forceinline__ void store_xyzz(xyzz_t *dst, const xyzz_t &v) {
     uint4 *d = reinterpret_cast<uint4 *>(dst);
     const uint4 *t = reinterpret_cast<const uint4 *>(&v);
 #pragma unroll
-    for (int i = 0; i < 12; i++) d[i] = t[i];
+    for (int i = 0; i < XYZZ_VEC; i++) d[i] = t[i];
 }
 __device__ __forceinline__ void load_affine(affine_t &d, const affine_t *src) {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
     uint4 *t = reinterpret_cast<uint4 *>(&d);
 #pragma unroll
-    for (int i = 0; i < 6; i++) t[i] = __ldg(s + i);
+    for (int i = 0; i < AFF_VEC; i++) t[i] = __ldg(s + i);
 }
 __device__ __forceinline__ void store_affine(affine_t *dst, const affine_t &v) {
     uint4 *d = reinterpret_cast<uint4 *>(dst);
     const uint4 *t = reinterpret_cast<const uint4 *>(&v);
 #pragma unroll
-    for (int i = 0; i < 6; i++) d[i] = t[i];
+    for (int i = 0; i < AFF_VEC; i++) d[i] = t[i];
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

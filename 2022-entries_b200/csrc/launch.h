@@ -19,15 +19,19 @@ template <class C> struct LaunchHot {
                            const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res);
 };
 template <class C> struct LaunchCold {
-    // mode 0: level 0 (through the piece table), 1: direct (S and T), 2: sum only
-    static void reduce_slices(int mode, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t m, xyzz_t *outS, xyzz_t *outT);
+    // n_out threads in blocks of `block` (n_out % block == 0); outT gets one entry per block
+    static void reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT);
+    static void block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out);
     static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, int extra_n, const xyzz_t *extra);
     static void double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp);
     static void batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst);
     static void gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp);
     static void gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out);
-    static void test_fp(int op, const fp *a, const fp *b, fp *r, uint32_t n);
-    static void test_ec(int op, xyzz_t *acc, const void *other, uint32_t n, int reps);
+    static void convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask);
+    static void export_points(cudaStream_t st, const affine_t *table0, uint32_t n, uint32_t *dst);
+    static void generator(fp &gx, fp &gy);      // host: the curve generator in the device representation
+    static void test_fp(int op, const fp_abi *a, const fp_abi *b, fp_abi *r, uint32_t n);
+    static void test_ec(int op, xyzz_abi_t *acc, const void *other, uint32_t n, int reps);
 };
 
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }

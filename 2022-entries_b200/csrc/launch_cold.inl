@@ -5,15 +5,16 @@
 namespace b200msm {
 
 template <class C>
-void LaunchCold<C>::reduce_slices(int mode, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t m, xyzz_t *outS, xyzz_t *outT) {
-    uint32_t blocks = cdiv(n_out, 128);
-    if (mode == 0) k_reduce_slices<C, true, false><<<blocks, 128, 0, st>>>(in, piece_off, n_out, m, outS, outT);
-    else if (mode == 1) k_reduce_slices<C, false, false><<<blocks, 128, 0, st>>>(in, nullptr, n_out, m, outS, outT);
-    else k_reduce_slices<C, false, true><<<blocks, 128, 0, st>>>(in, nullptr, n_out, m, outS, nullptr);
+void LaunchCold<C>::reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT) {
+    if (indirect) k_reduce_slices<C, true><<<n_out / block, block, 0, st>>>(in, piece_off, m, outS, outT);
+    else k_reduce_slices<C, false><<<n_out / block, block, 0, st>>>(in, nullptr, m, outS, outT);
+}
+template <class C> void LaunchCold<C>::block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out) {
+    k_block_sum<C><<<ngroups, group < 128 ? group : 128, 0, st>>>(in, group, out);
 }
 template <class C>
 void LaunchCold<C>::finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, int extra_n, const xyzz_t *extra) {
-    k_finalize<C><<<1, 32, 0, st>>>(a, out_xyzz, out_jac, extra_n, extra);
+    k_finalize<C><<<1, 32 * 8, 0, st>>>(a, out_xyzz, out_jac, extra_n, extra);
 }
 template <class C> void LaunchCold<C>::double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp) {
     k_double_n<C><<<cdiv(n, 128), 128, 0, st>>>(src, n, k, tmp);
@@ -28,10 +29,16 @@ void LaunchCold<C>::gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint
 template <class C> void LaunchCold<C>::gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out) {
     k_gen_scalars<C><<<cdiv(n, 256), 256, 0, st>>>(n, seed, out);
 }
-template <class C> void LaunchCold<C>::test_fp(int op, const fp *a, const fp *b, fp *r, uint32_t n) {
+template <class C> void LaunchCold<C>::convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask) {
+    k_convert_points<C><<<cdiv(n, 128), 128, 0, st>>>(src, n, stride, table0, infmask);
+}
+template <class C> void LaunchCold<C>::export_points(cudaStream_t st, const affine_t *table0, uint32_t n, uint32_t *dst) {
+    k_export_points<C><<<cdiv(n, 128), 128, 0, st>>>(table0, n, dst);
+}
+template <class C> void LaunchCold<C>::test_fp(int op, const fp_abi *a, const fp_abi *b, fp_abi *r, uint32_t n) {
     k_test_fp<C><<<cdiv(n, 128), 128>>>(op, a, b, r, n);
 }
-template <class C> void LaunchCold<C>::test_ec(int op, xyzz_t *acc, const void *other, uint32_t n, int reps) {
+template <class C> void LaunchCold<C>::test_ec(int op, xyzz_abi_t *acc, const void *other, uint32_t n, int reps) {
     k_test_ec<C><<<cdiv(n, 64), 64>>>(op, acc, other, n, reps);
 }
 

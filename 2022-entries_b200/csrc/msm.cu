@@ -24,9 +24,9 @@ static thread_local std::string g_create_error;
     } while (0)
 
 struct red_step_t {
-    bool indirect, sum_only;
+    int kind;                 // 0: reduce_slices through the piece table, 1: reduce_slices, 2: block_sum
     const xyzz_t *in;
-    uint32_t n_out, m;
+    uint32_t n_out, block, m; // block_sum: n_out groups of m inputs
     xyzz_t *outS, *outT;
 };
 
@@ -145,26 +145,23 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     CK(dmalloc(&ctx->part_xyzz, 1));
 
     // bucket-reduction plan (see k_reduce_slices): sizes first, then carve red_buf
-    struct lvl { uint32_t n_in, m, n_out; };
-    std::vector<lvl> main_lv;
-    uint32_t per_f = 1u << (ctx->c - 1);
+    struct lvl { uint32_t n_in, m, n_out, block, nT; };
+    std::vector<lvl> lv;
     {
-        uint32_t cur = per_f;
+        uint32_t cur = 1u << (ctx->c - 1);
         bool first = true;
         while (first || cur > 32) {
-            uint32_t m = cur / 32; if (m > 64) m = 64; if (m < 1) m = 1;
-            main_lv.push_back({cur, m, cur / m});
-            cur /= m;
+            uint32_t m = cur >= 256 ? 8 : cur / 32;
+            if (m < 1) m = 1;
+            uint32_t n_out = cur / m, block = n_out < 128 ? n_out : 128;
+            lv.push_back({cur, m, n_out, block, n_out / block});
+            cur = n_out;
             first = false;
         }
     }
+    const uint32_t F = ctx->F;
     size_t need = 0;
-    for (auto &l : main_lv) {
-        need += 2 * (size_t)l.n_out;          // S and T
-        uint32_t t = l.n_out;
-        while (t > 32) { uint32_t m = t / 32; if (m > 64) m = 64; t /= m; need += t; }
-    }
-    need *= ctx->F;
+    for (auto &l : lv) need += (size_t)F * (l.n_out + l.nT + (l.nT > 32 ? 32 : 0));
     CK(dmalloc(&ctx->red_buf, need + 1));
     xyzz_t *bump = ctx->red_buf;
     auto take = [&](size_t cnt) { xyzz_t *p = bump; bump += cnt; return p; };
@@ -172,34 +169,27 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     fin_args_t &fin = ctx->fin;
     memset(&fin, 0, sizeof(fin));
     fin.F = ctx->F; fin.c = ctx->c;
-    const uint32_t F = ctx->F;
     const xyzz_t *cur_arr = ctx->res;
     uint32_t shift = 0;
-    struct pend { xyzz_t *arr; uint32_t n; uint32_t shift; };
-    std::vector<pend> pending;
-    for (size_t li = 0; li < main_lv.size(); li++) {
-        lvl &l = main_lv[li];
-        xyzz_t *S = take((size_t)F * l.n_out), *Tt = take((size_t)F * l.n_out);
-        ctx->red_steps.push_back({li == 0, false, cur_arr, F * l.n_out, l.m, S, Tt});
-        pending.push_back({Tt, l.n_out, shift});
+    for (size_t li = 0; li < lv.size(); li++) {
+        lvl &l = lv[li];
+        xyzz_t *S = take((size_t)F * l.n_out), *Tt = take((size_t)F * l.nT);
+        ctx->red_steps.push_back({li == 0 ? 0 : 1, cur_arr, F * l.n_out, l.block, l.m, S, Tt});
+        uint32_t nT = l.nT;
+        if (nT > 32) {
+            xyzz_t *T2 = take((size_t)F * 32);
+            ctx->red_steps.push_back({2, Tt, F * 32, 0, nT / 32, T2, nullptr});
+            Tt = T2; nT = 32;
+        }
+        if (fin.nterms >= FIN_MAX_TERMS - 2) return ctx->fail(-1, "reduction plan has too many terms");
+        fin.term[fin.nterms++] = {Tt, nT, nT, shift, 0};                 // 2^shift * sum_t T_t of this level
         uint32_t lg = 0; while ((1u << lg) < l.m) lg++;
         shift += lg;
         cur_arr = S;
     }
-    uint32_t last_n = main_lv.back().n_out;
-    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, 0, 0};          // sum of all buckets
-    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, shift, 1};      // 2^shift * W0(S_last)
-    for (auto &p : pending) {
-        xyzz_t *arr = p.arr; uint32_t t = p.n;
-        while (t > 32) {
-            uint32_t m = t / 32; if (m > 64) m = 64;
-            xyzz_t *o = take((size_t)F * (t / m));
-            ctx->red_steps.push_back({false, true, arr, F * (t / m), m, o, nullptr});
-            arr = o; t /= m;
-        }
-        if (fin.nterms >= FIN_MAX_TERMS) return ctx->fail(-1, "reduction plan has too many terms");
-        fin.term[fin.nterms++] = {arr, t, t, p.shift, 0};
-    }
+    uint32_t last_n = lv.back().n_out;
+    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, 0, 0};            // sum of all buckets
+    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, shift, 1};        // 2^shift * W0(S_last)
     return 0;
 }
 
@@ -249,19 +239,21 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
     return 0;
 }
 
-// generator in Montgomery form (P1B/nickray/driver/bls12-377/src/curves/g1.rs:159-165)
+// generator in the device representation (P1B/nickray/driver/bls12-377/src/curves/g1.rs:159-165)
 static void generator(int curve, fp &gx, fp &gy) {
     static const uint32_t g377x[12] = {0xb21be9efu, 0xeab9b16eu, 0xffcd394eu, 0xd5481512u, 0xbd37cb5cu, 0x188282c8u, 0xaa9d41bbu, 0x85951e2cu, 0xbf87ff54u, 0xc8fc6225u, 0xfe740a67u, 0x008848deu};
     static const uint32_t g377y[12] = {0x559c8ea6u, 0xfd82de55u, 0x34a9591au, 0xc2fe3d36u, 0x4fb82305u, 0x6d182ad4u, 0xca3e52d9u, 0xbd7fb348u, 0x30afeec4u, 0x1f674f5du, 0xc5102effu, 0x01914a69u};
     static const uint32_t g381x[12] = {0xdb22c6bbu, 0xfb3af00au, 0xf97a1aefu, 0x6c55e83fu, 0x171bac58u, 0xa14e3a3fu, 0x9774b905u, 0xc3688c4fu, 0x4fa9ac0fu, 0x2695638cu, 0x3197d794u, 0x17f1d3a7u};
     static const uint32_t g381y[12] = {0x46c5e7e1u, 0x0caa2329u, 0xa2888ae4u, 0xd03cc744u, 0x2c04b3edu, 0x00db18cbu, 0xd5d00af6u, 0xfcf5e095u, 0x741d8ae4u, 0xa09e30edu, 0xe3aaa0f1u, 0x08b3f481u};
-    // canonical -> Montgomery on the host (schoolbook, only here): x * 2^384 mod p by 384 modular doublings
+    // canonical -> x * 2^392 mod p on the host (schoolbook, only here: 392 modular doublings), then 28-bit limbs
     auto to_mont = [&](const uint32_t *v, fp &out) {
         uint32_t a[13];
         for (int i = 0; i < 12; i++) a[i] = v[i];
         a[12] = 0;
-        auto p = [&](int i) { return curve == 0 ? Bls12_377::p(i) : Bls12_381::p(i); };
-        for (int s = 0; s < 384; s++) {
+        static const uint32_t p377[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu, 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+        static const uint32_t p381[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        auto p = [&](int i) { return curve == 0 ? p377[i] : p381[i]; };
+        for (int s = 0; s < FP_LIMBS * FP_BITS; s++) {
             uint32_t carry = 0;
             for (int i = 0; i < 13; i++) { uint32_t nc = a[i] >> 31; a[i] = (a[i] << 1) | carry; carry = nc; }
             // a >= p ? a -= p
@@ -269,7 +261,9 @@ static void generator(int curve, fp &gx, fp &gy) {
             if (!ge) { ge = true; for (int i = 11; i >= 0; i--) if (a[i] != p(i)) { ge = a[i] > p(i); break; } }
             if (ge) { uint64_t br = 0; for (int i = 0; i < 12; i++) { uint64_t t = (uint64_t)a[i] - p(i) - br; a[i] = (uint32_t)t; br = (t >> 32) & 1; } a[12] -= (uint32_t)br; }
         }
-        for (int i = 0; i < 12; i++) out.l[i] = a[i];
+        fp_abi packed;
+        for (int i = 0; i < 12; i++) packed.w[i] = a[i];
+        Fp<Bls12_377>::repack_from_abi(out, packed);      // pure bit slicing, curve-independent
     };
     to_mont(curve == 0 ? g377x : g381x, gx);
     to_mont(curve == 0 ? g377y : g381y, gy);
@@ -315,7 +309,8 @@ template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_de
     cudaEventRecord(ctx->ev[4], st);
     // bucket reduction
     for (const red_step_t &s : ctx->red_steps) {
-        LaunchCold<C>::reduce_slices(s.indirect ? 0 : (s.sum_only ? 2 : 1), st, s.in, ctx->piece_off, s.n_out, s.m, s.outS, s.outT);
+        if (s.kind == 2) LaunchCold<C>::block_sum(st, s.in, s.n_out, s.m, s.outS);
+        else LaunchCold<C>::reduce_slices(s.kind == 0, st, s.in, ctx->piece_off, s.n_out, s.block, s.m, s.outS, s.outT);
         launches++;
     }
     cudaEventRecord(ctx->ev[5], st);
@@ -413,7 +408,8 @@ int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uin
     for (uint64_t first = 0; first < n; first += chunk) {
         uint64_t cnt = n - first < chunk ? n - first : chunk;
         CK(cudaMemcpyAsync(raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), cudaMemcpyHostToDevice, ctx->stream));
-        k_convert_points<<<cdiv(cnt, 256), 256, 0, ctx->stream>>>(raw, (uint32_t)cnt, (uint32_t)stride, ctx->tables + first, ctx->infmask + first / 32);
+        if (ctx->curve == 0) LaunchCold<Bls12_377>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, ctx->tables + first, ctx->infmask + first / 32);
+        else LaunchCold<Bls12_381>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, ctx->tables + first, ctx->infmask + first / 32);
         CK(cudaStreamSynchronize(ctx->stream));
     }
     cudaFree(raw);
@@ -436,7 +432,13 @@ int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uin
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!affine96_host || first + n > ctx->n) return ctx->fail(-1, "b200msm_get_bases: bad argument");
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(affine96_host, ctx->tables + first, (size_t)n * 96, cudaMemcpyDeviceToHost));
+    uint32_t *tmp = nullptr;
+    CK(cudaMalloc((void **)&tmp, (size_t)n * 96));
+    if (ctx->curve == 0) LaunchCold<Bls12_377>::export_points(ctx->stream, ctx->tables + first, (uint32_t)n, tmp);
+    else LaunchCold<Bls12_381>::export_points(ctx->stream, ctx->tables + first, (uint32_t)n, tmp);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(affine96_host, tmp, (size_t)n * 96, cudaMemcpyDeviceToHost));
+    cudaFree(tmp);
     return 0;
 }
 
@@ -531,7 +533,7 @@ static int test_fail(const char *what, cudaError_t e) {
 
 int b200msm_test_fp_op(int curve, int op, const void *a, const void *b, void *r, uint64_t n) {
     if (!a || !b || !r || n == 0 || (curve != 0 && curve != 1)) return -1;
-    fp *da, *db, *dr;
+    fp_abi *da, *db, *dr;
     size_t bytes = (size_t)n * 48;
     TCK(cudaMalloc((void **)&da, bytes)); TCK(cudaMalloc((void **)&db, bytes)); TCK(cudaMalloc((void **)&dr, bytes));
     TCK(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice)); TCK(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
@@ -545,7 +547,7 @@ int b200msm_test_fp_op(int curve, int op, const void *a, const void *b, void *r,
 
 int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t n, int reps) {
     if (!acc || n == 0 || (curve != 0 && curve != 1) || op < 0 || op > 3 || (op != 2 && !other)) return -1;
-    xyzz_t *dacc; void *doth = nullptr;
+    xyzz_abi_t *dacc; void *doth = nullptr;
     size_t ob = (op == 1 ? 192 : 96) * (size_t)n;
     TCK(cudaMalloc((void **)&dacc, (size_t)n * 192));
     TCK(cudaMemcpy(dacc, acc, (size_t)n * 192, cudaMemcpyHostToDevice));

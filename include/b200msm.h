@@ -66,8 +66,10 @@ int b200msm_msm_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, vo
  * results are in place.  Scalar upload of batch b+1 overlaps the compute of batch b. */
 int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uint64_t batches, void *out_jacobian_host);
 
-/* Point sharding across GPUs: the local shard's sum as one 192-byte XYZZ record in device memory (asynchronous),
- * and the combine step run after the all-gather: sum `count` XYZZ records -> 144-byte Jacobian (device memory). */
+/* Point sharding across GPUs: the local shard's sum as one B200MSM_PARTIAL_BYTES record in device memory
+ * (asynchronous; XYZZ coordinates in the device representation, opaque to the caller), and the combine step run after
+ * the all-gather: sum `count` such records -> 144-byte Jacobian (device memory). */
+#define B200MSM_PARTIAL_BYTES 224
 int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev);
 int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev);
 
@@ -80,8 +82,9 @@ int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]);
 int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]);
 
 /* Element-wise device arithmetic on host arrays, for the parity tests of the field and curve layers.
- * fp op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 to-Montgomery, 6 from-Montgomery (48-byte elements, canonical out).
- * ec op: 0 acc += affine(96 B), 1 acc += xyzz(192 B), 2 acc = 2 acc, 3 acc = 2 affine; acc is XYZZ (192 B). */
+ * Operands and results are arkworks field elements (48 bytes, Montgomery R = 2^384, canonical); the library converts
+ * to and from its device representation.  fp op: 0 mul, 1 add, 2 sub, 3 sqr, 4 inv, 5 representation round trip.
+ * ec op: 0 acc += affine(96 B), 1 acc += xyzz(192 B), 2 acc = 2 acc, 3 acc = 2 affine; acc is XYZZ (4 x 48 B). */
 int b200msm_test_fp_op(int curve, int op, const void *a, const void *b, void *r, uint64_t n);
 int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t n, int reps);
 

@@ -6,70 +6,88 @@
 #include "../../2022-entries_b200/csrc/ec.cuh"
 using namespace b200msm;
 
-template <class C> static void fp_ops(int op, const fp *a, const fp *b, fp *r, size_t n) {
+// All entry points take and return arkworks-ABI field elements (48 bytes, R = 2^384, canonical) and convert to the
+// device representation (14 x 28-bit limbs, R = 2^392) with the same from_abi / to_abi the kernels use.
+template <class C> static void fp_ops(int op, const fp_abi *a, const fp_abi *b, fp_abi *r, size_t n) {
     typedef Fp<C> F;
     for (size_t i = 0; i < n; i++) {
-        fp t;
+        fp x, y, t;
+        F::from_abi(x, a[i]);
+        F::from_abi(y, b[i]);
         switch (op) {
-        case 0: F::mul(t, a[i], b[i]); break;
-        case 1: F::add(t, a[i], b[i]); break;
-        case 2: F::template sub<2>(t, a[i], b[i]); break;
-        case 3: F::sqr(t, a[i]); break;
-        case 4: F::inv(t, a[i]); break;
-        case 5: F::to_mont(t, a[i]); break;
-        case 6: F::from_mont(t, a[i]); break;
-        default: t = a[i];
+        case 0: F::mul(t, x, y); break;
+        case 1: F::add(t, x, y); break;
+        case 2: F::template sub<2>(t, x, y); break;
+        case 3: F::sqr(t, x); break;
+        case 4: F::inv(t, x); break;
+        default: t = x;                       // 5: ABI round trip
         }
-        F::reduce(t);
-        r[i] = t;
+        F::to_abi(r[i], t);
     }
 }
-template <class C> static void canon(xyzz_t &q) {
+template <class C> static void load_xyzz_abi(xyzz_t &q, const xyzz_abi_t &a) {
     typedef Fp<C> F;
-    F::reduce(q.x); F::reduce(q.y); F::reduce(q.zz); F::reduce(q.zzz);
+    F::from_abi(q.x, a.x); F::from_abi(q.y, a.y); F::from_abi(q.zz, a.zz); F::from_abi(q.zzz, a.zzz);
 }
 // op 0: acc += aff (madd); 1: acc += other (add); 2: acc = 2 acc; 3: acc = 2*aff
-template <class C> static void ec_ops(int op, xyzz_t *acc, const void *other, size_t n, int reps) {
-    typedef Ec<C> E;
+template <class C> static void ec_ops(int op, xyzz_abi_t *acc, const void *other, size_t n, int reps) {
+    typedef Ec<C> E; typedef Fp<C> F;
     for (size_t i = 0; i < n; i++) {
+        xyzz_t q; load_xyzz_abi<C>(q, acc[i]);
+        affine_t a; xyzz_t o;
+        if (op == 0 || op == 3) { F::from_abi(a.x, ((const affine_abi_t *)other)[i].x); F::from_abi(a.y, ((const affine_abi_t *)other)[i].y); }
+        if (op == 1) load_xyzz_abi<C>(o, ((const xyzz_abi_t *)other)[i]);
         for (int k = 0; k < reps; k++) {
             switch (op) {
-            case 0: E::madd(acc[i], ((const affine_t *)other)[i].x, ((const affine_t *)other)[i].y); break;
-            case 1: E::add(acc[i], ((const xyzz_t *)other)[i]); break;
-            case 2: E::dbl(acc[i]); break;
-            case 3: E::dbl_affine(acc[i], ((const affine_t *)other)[i].x, ((const affine_t *)other)[i].y); break;
+            case 0: E::madd(q, a.x, a.y); break;
+            case 1: E::add(q, o); break;
+            case 2: E::dbl(q); break;
+            case 3: E::dbl_affine(q, a.x, a.y); break;
             }
         }
-        canon<C>(acc[i]);
+        F::to_abi(acc[i].x, q.x); F::to_abi(acc[i].y, q.y); F::to_abi(acc[i].zz, q.zz); F::to_abi(acc[i].zzz, q.zzz);
     }
 }
-// lazy-bound stress: multiply k1*p + a by k2*p + b (same residues, larger representatives)
-template <class C> static void fp_mul_lazy(const fp *a, const fp *b, fp *r, size_t n, int k1, int k2) {
+// lazy-bound stress: multiply (a + k1 p) by (b + k2 p) -- same residues, larger representatives -- and report
+// whether the documented output bound (< 2p) held
+template <class C> static int fp_mul_lazy(const fp_abi *a, const fp_abi *b, fp_abi *r, size_t n, int k1, int k2) {
     typedef Fp<C> F;
+    int violations = 0;
     for (size_t i = 0; i < n; i++) {
-        fp x = a[i], y = b[i], pp;
-        for (int j = 0; j < 12; j++) pp.l[j] = C::p(j);
+        fp x, y, pp;
+        F::from_abi(x, a[i]); F::from_abi(y, b[i]);
+        for (int j = 0; j < FP_LIMBS; j++) pp.l[j] = C::p(j);
         for (int k = 0; k < k1; k++) F::add(x, x, pp);
         for (int k = 0; k < k2; k++) F::add(y, y, pp);
         fp t; F::mul(t, x, y);
-        // record whether the documented bound (< 2p) held: subtract 2p must borrow
-        fp chk = t; F::template csub<2>(chk);
-        r[i] = t;
-        F::reduce(r[i]);
-        if (memcmp(&chk, &t, sizeof(fp)) != 0) r[i].l[11] |= 0x80000000u;   // flag bound violation
+        fp chk = t; F::csub_p(chk); F::csub_p(chk);          // < 2p  <=>  two conditional subtractions reach [0, p)
+        fp canon = t; F::reduce(canon);
+        if (memcmp(&chk, &canon, sizeof(fp)) != 0) violations++;
+        F::to_abi(r[i], t);
     }
+    return violations;
+}
+// curve constants as plain little-endian integers for the test to re-derive: p, one, cin, cout (4 x 56 bytes of limbs)
+template <class C> static void constants(uint32_t *out) {
+    for (int i = 0; i < FP_LIMBS; i++) { out[i] = C::p(i); out[14 + i] = C::one(i); out[28 + i] = C::cin(i); out[42 + i] = C::cout(i); }
+    out[56] = C::INV; out[57] = C::P0INV;
+    for (int k = 0; k < 16; k++) for (int i = 0; i < FP_LIMBS; i++) out[64 + k * 14 + i] = kp_dom<C>(k + 1, i);
 }
 extern "C" {
 int emul_fp_op(int curve, int op, const void *a, const void *b, void *r, size_t n) {
-    if (curve == 0) fp_ops<Bls12_377>(op, (const fp *)a, (const fp *)b, (fp *)r, n); else fp_ops<Bls12_381>(op, (const fp *)a, (const fp *)b, (fp *)r, n);
+    if (curve == 0) fp_ops<Bls12_377>(op, (const fp_abi *)a, (const fp_abi *)b, (fp_abi *)r, n); else fp_ops<Bls12_381>(op, (const fp_abi *)a, (const fp_abi *)b, (fp_abi *)r, n);
     return 0;
 }
 int emul_ec_op(int curve, int op, void *acc, const void *other, size_t n, int reps) {
-    if (curve == 0) ec_ops<Bls12_377>(op, (xyzz_t *)acc, other, n, reps); else ec_ops<Bls12_381>(op, (xyzz_t *)acc, other, n, reps);
+    if (curve == 0) ec_ops<Bls12_377>(op, (xyzz_abi_t *)acc, other, n, reps); else ec_ops<Bls12_381>(op, (xyzz_abi_t *)acc, other, n, reps);
     return 0;
 }
 int emul_fp_mul_lazy(int curve, const void *a, const void *b, void *r, size_t n, int k1, int k2) {
-    if (curve == 0) fp_mul_lazy<Bls12_377>((const fp *)a, (const fp *)b, (fp *)r, n, k1, k2); else fp_mul_lazy<Bls12_381>((const fp *)a, (const fp *)b, (fp *)r, n, k1, k2);
+    return curve == 0 ? fp_mul_lazy<Bls12_377>((const fp_abi *)a, (const fp_abi *)b, (fp_abi *)r, n, k1, k2)
+                      : fp_mul_lazy<Bls12_381>((const fp_abi *)a, (const fp_abi *)b, (fp_abi *)r, n, k1, k2);
+}
+int emul_constants(int curve, uint32_t *out) {
+    if (curve == 0) constants<Bls12_377>(out); else constants<Bls12_381>(out);
     return 0;
 }
 }
