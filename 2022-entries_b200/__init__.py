@@ -65,6 +65,8 @@ def lib():
     L.b200msm_sync.argtypes = [vp]
     L.b200msm_get_info.argtypes = [vp, ctypes.POINTER(u64)]
     L.b200msm_get_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.b200msm_reset_stage_stats.argtypes = [vp]
+    L.b200msm_get_stage_ms_sum.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]
     L.b200msm_test_fp_op.argtypes = [i32, i32, vp, vp, vp, u64]
     L.b200msm_test_ec_op.argtypes = [i32, i32, vp, vp, u64, i32]
     L.mult_pippenger_init.argtypes = [ctypes.POINTER(_FfiContext), vp, sz, sz]
@@ -89,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
     "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
-    "b200msm_get_stage_ms", "b200msm_test_fp_op", "b200msm_test_ec_op", "mult_pippenger_init", "mult_pippenger_inf",
+    "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "mult_pippenger_init", "mult_pippenger_inf",
     "mult_pippenger_free", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
 ]
 
@@ -121,9 +123,20 @@ class MultiScalarMultContext:
         self.ffi = _FfiContext(None)
         self.npoints = 0
 
+    @classmethod
+    def from_engine(cls, engine):
+        """A harness context over an existing native engine (bench.py: bases generated on the device instead of
+        6.5 GiB of host records).  The engine keeps ownership."""
+        ctx = cls()
+        ctx.ffi.context = engine.h.value
+        ctx.npoints = engine.n
+        ctx.borrowed = True
+        return ctx
+
     def free(self):
-        if self.ffi.context:
+        if self.ffi.context and not getattr(self, "borrowed", False):
             lib().mult_pippenger_free(ctypes.byref(self.ffi))
+        self.ffi.context = None
 
     def __del__(self):
         try:
@@ -144,10 +157,14 @@ def multi_scalar_mult_init(points):
 
 
 def multi_scalar_mult(context, points, scalars):
-    """scalars: batches * n 32-byte integers.  Returns uint8[batches, 144] Jacobian results."""
-    pts = _as_u8(points, AFFINE_BYTES, "points")
+    """scalars: batches * n 32-byte integers.  Returns uint8[batches, 144] Jacobian results.
+    points may be None for a context made by from_engine (the C side ignores the argument, as the reference does)."""
     sc = _as_u8(scalars, SCALAR_BYTES, "scalars")
-    npoints = pts.size // AFFINE_BYTES
+    if points is None:
+        pts, npoints = np.zeros(1, np.uint8), context.npoints
+    else:
+        pts = _as_u8(points, AFFINE_BYTES, "points")
+        npoints = pts.size // AFFINE_BYTES
     nscalars = sc.size // SCALAR_BYTES
     if npoints == 0 or nscalars % npoints != 0:
         raise MsmError("length mismatch")                            # the Rust shim panics with the same message
@@ -271,6 +288,16 @@ class Engine:
         lib().b200msm_get_info(self.h, a)
         keys = ("n", "window_bits", "windows", "tables", "folded_windows", "buckets", "lmax", "launches")
         return dict(zip(keys, [int(v) for v in a]))
+
+    def reset_stage_stats(self):
+        self._ck(lib().b200msm_reset_stage_stats(self.h), "reset_stage_stats")
+
+    def stage_ms_sum(self):
+        """(per-stage milliseconds summed over the MSMs since reset_stage_stats, number of MSMs covered)."""
+        a = (ctypes.c_float * 6)()
+        k = ctypes.c_uint64()
+        self._ck(lib().b200msm_get_stage_ms_sum(self.h, a, ctypes.byref(k)), "get_stage_ms_sum")
+        return dict(zip(self.STAGES, [float(v) for v in a])), int(k.value)
 
     def stage_ms(self):
         a = (ctypes.c_float * 6)()

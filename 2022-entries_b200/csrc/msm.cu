@@ -57,7 +57,10 @@ struct b200msm_ctx {
     uint64_t out_dev_cap = 0;
     std::vector<red_step_t> red_steps;
     fin_args_t fin;
-    cudaEvent_t ev[7] = {};
+    static const int EV_RING = 32;
+    cudaEvent_t evr[EV_RING][7] = {};   // stage boundaries of the last EV_RING MSMs
+    uint64_t ev_steps = 0;              // MSMs recorded since the last stats reset
+    cudaEvent_t *ev = evr[0];           // the set the current / last MSM records into
     cudaEvent_t ev_copied[2] = {}, ev_free[2] = {};
 
     int fail(int code, const std::string &msg) {
@@ -276,6 +279,8 @@ template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_de
     const uint32_t n = (uint32_t)ctx->n, nb = ctx->nbuckets, lmax = ctx->lmax;
     const uint32_t *sc = (const uint32_t *)scalars_dev;
     int launches = 0;
+    ctx->ev = ctx->evr[ctx->ev_steps % b200msm_ctx::EV_RING];
+    ctx->ev_steps++;
     cudaEventRecord(ctx->ev[0], st);
     if (!hist_done) {
         CK(cudaMemsetAsync(ctx->counts, 0, ((size_t)nb + 1) * 4, st));
@@ -355,7 +360,7 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+    for (int r = 0; r < b200msm_ctx::EV_RING; r++) for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->evr[r][i]);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming); }
     if (e != cudaSuccess) {
         g_create_error = std::string("b200msm_create: ") + cudaGetErrorString(e);
@@ -372,7 +377,7 @@ int b200msm_destroy(b200msm_ctx *ctx) {
     cudaDeviceSynchronize();
     ctx->free_plan();
     if (ctx->out_dev) cudaFree(ctx->out_dev);
-    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto &row : ctx->evr) for (auto &e : row) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -520,6 +525,27 @@ int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]) {
     if (!stage_ms) return -1;
     CK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(&stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return 0;
+}
+
+int b200msm_reset_stage_stats(b200msm_ctx *ctx) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ev_steps = 0;
+    return 0;
+}
+
+int b200msm_get_stage_ms_sum(b200msm_ctx *ctx, float stage_ms_sum[6], uint64_t *steps) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!stage_ms_sum || !steps) return -1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    uint64_t cnt = ctx->ev_steps < (uint64_t)b200msm_ctx::EV_RING ? ctx->ev_steps : (uint64_t)b200msm_ctx::EV_RING;
+    for (int i = 0; i < 6; i++) stage_ms_sum[i] = 0.f;
+    for (uint64_t k = 0; k < cnt; k++) {
+        cudaEvent_t *ev = ctx->evr[(ctx->ev_steps - 1 - k) % b200msm_ctx::EV_RING];
+        for (int i = 0; i < 6; i++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); stage_ms_sum[i] += ms; }
+    }
+    *steps = cnt;
     return 0;
 }
 

@@ -1,0 +1,99 @@
+"""Point sharding across the GPUs of one box (BASELINE.json config 3).
+
+MSM is linear in the point set:  sum_i s_i P_i = sum_g  sum_{i in shard g} s_i P_i.  Rank g keeps the contiguous slice
+[g*n/G, (g+1)*n/G) of the bases resident (tables built at init) and receives the same slice of every scalar batch.
+One exchange per MSM: each rank's partial sum (one XYZZ record, 224 bytes) is all-gathered as bytes -- NCCL has no
+reduction operator for curve addition, so the north-star's "allreduce of the partial sums" is an all-gather followed
+by the same G-point sum on every rank -- and every rank ends with the full result, like an all-reduce.
+
+The reference has no multi-GPU path at all (device 0 hard-coded: P1A/yrrid/yrrid-msm/MSM.cu:302,
+P1A/matter-labs/src/lib.rs:86).
+
+The per-rank engine is injected so that the host logic (slicing, exchange, combine order) runs under gloo on CPU in the
+tests, with a checker standing in for the CUDA engine; the product path constructs it over `Engine` (libb200msm.so).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous slice of rank `rank`; n must divide evenly (the harness sizes are powers of two)."""
+    if n % world:
+        raise ValueError(f"{n} points do not shard evenly over {world} ranks")
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+class CudaShardBackend:
+    """One rank's engine: partial sums and the combine step run in libb200msm.so on this rank's GPU."""
+
+    def __init__(self, engine, torch_stream=None):
+        self.e = engine
+        self.device = torch.device("cuda", engine.device)
+        self.stream = torch_stream or torch.cuda.Stream(self.device)
+        engine.set_stream(self.stream.cuda_stream)
+        from . import PARTIAL_BYTES, PROJECTIVE_BYTES
+        self.partial_bytes, self.out_bytes = PARTIAL_BYTES, PROJECTIVE_BYTES
+        self.n = engine.n
+        self.dev_scalars = None
+
+    def new_buffer(self, nbytes):
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+
+    def upload(self, scalars_host):
+        """Pinned host tensor (n_local*32 bytes) -> device, on the engine's stream."""
+        if self.dev_scalars is None:
+            self.dev_scalars = torch.empty(self.n * 32, dtype=torch.uint8, device=self.device)
+        with torch.cuda.stream(self.stream):
+            self.dev_scalars.copy_(scalars_host, non_blocking=True)
+        return self.dev_scalars
+
+    def partial(self, scalars_dev, out):
+        self.e.msm_partial_device(scalars_dev.data_ptr(), self.n, out.data_ptr())
+
+    def full(self, scalars_dev, out):
+        self.e.msm_device(scalars_dev.data_ptr(), self.n, out.data_ptr())
+
+    def combine(self, gathered, count, out):
+        self.e.combine_device(gathered.data_ptr(), count, out.data_ptr())
+
+
+class ShardedMsm:
+    """multi_scalar_mult over G ranks.  Every rank calls msm() with ITS slice of the scalars and gets the full result."""
+
+    def __init__(self, backend, group=None):
+        self.b = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.partial = backend.new_buffer(backend.partial_bytes)
+        self.gathered = backend.new_buffer(backend.partial_bytes * self.world)
+        self.out = backend.new_buffer(backend.out_bytes)
+
+    def msm_device(self, scalars_dev):
+        """scalars already on this rank's device.  Asynchronous on the backend's stream; returns the device buffer
+        holding the 144-byte Jacobian result (identical on every rank)."""
+        b = self.b
+        if self.world == 1:
+            b.full(scalars_dev, self.out)
+            return self.out
+        b.partial(scalars_dev, self.partial)
+        stream = getattr(b, "stream", None)
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
+        else:
+            dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
+        b.combine(self.gathered, self.world, self.out)
+        return self.out
+
+    def msm(self, scalars_host):
+        """End-to-end call: this rank's scalar slice in (pinned) host memory -> 144-byte result on the host."""
+        dev = self.b.upload(scalars_host)
+        out = self.msm_device(dev)
+        stream = getattr(self.b, "stream", None)
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                host = out.to("cpu", non_blocking=False)
+            return host
+        return out.clone()

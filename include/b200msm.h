@@ -80,6 +80,10 @@ int b200msm_sync(b200msm_ctx *ctx);
  * accumulate, bucket reduce, finalize (CUDA events on the context's stream; valid after b200msm_sync). */
 int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]);
 int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]);
+/* The same six stage times summed over the MSMs run since b200msm_reset_stage_stats (at most the last 32 are kept);
+ * *steps = how many MSMs the sums cover.  bench.py derives the per-launch duration of the accumulate kernel from it. */
+int b200msm_reset_stage_stats(b200msm_ctx *ctx);
+int b200msm_get_stage_ms_sum(b200msm_ctx *ctx, float stage_ms_sum[6], uint64_t *steps);
 
 /* Element-wise device arithmetic on host arrays, for the parity tests of the field and curve layers.
  * Operands and results are arkworks field elements (48 bytes, Montgomery R = 2^384, canonical); the library converts

@@ -1,0 +1,62 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/b200msm.h
+declares, argument errors surface without a GPU, and the product path has no CPU fallback."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def M():
+    import __graft_entry__ as g
+    m = g.load_package()
+    if not os.path.exists(m.LIB_PATH):
+        g.build()
+    return m
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "b200msm.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", hdr)
+    return sorted({n for n in names if n.startswith(("b200msm_", "mult_pippenger", "MSM"))})
+
+
+def test_library_exports_every_declared_symbol(M):
+    L = ctypes.CDLL(M.LIB_PATH)
+    decl = declared_symbols()
+    assert len(decl) >= 24
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in include/b200msm.h but not exported"
+    assert sorted(M.EXPORTED_SYMBOLS) == decl
+
+
+def test_no_cpu_fallback(M):
+    """Without a CUDA device every entry point fails loudly (-2 / RustError / NULL); nothing computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(M.MsmError):
+        M.Engine()
+    pts = np.zeros((4, 104), np.uint8)
+    with pytest.raises(M.MsmError):
+        M.multi_scalar_mult_init(pts)
+    with pytest.raises(M.MsmError):
+        M.YrridContext()
+
+
+def test_bad_arguments(M):
+    L = M.lib()
+    h = ctypes.c_void_p()
+    assert L.b200msm_create(ctypes.byref(h), 7, 0, 0, 0) == -1
+    assert L.b200msm_create(None, 0, 0, 0, 0) == -1
+    assert L.b200msm_destroy(None) == -1
+    assert L.MSMFreeContext(None) == -1
+    assert L.MSMRun(None, None, None, 0) == -1
+    assert L.MSMAllocContext(0, 1) is None
+    with pytest.raises(M.MsmError):
+        M.multi_scalar_mult(M.MultiScalarMultContext(), np.zeros((4, 104), np.uint8), np.zeros((5, 32), np.uint8))   # length mismatch

@@ -1,0 +1,161 @@
+"""CPU checks of the device field / curve headers (csrc/fp.cuh, csrc/ec.cuh) compiled for the host.
+
+The headers are plain C++ apart from the __device__ markers, so g++ builds them (tests/host_emul/emul.cpp) and the
+limb-level algorithms (14 x 28-bit reduced radix, R = 2^392, lazy reduction bounds) are compared with the CPU oracle
+without a GPU.  The GPU parity tests (test_gpu_parity.py) repeat the comparison on the real kernels.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import ref_bigint as RB
+
+HERE = os.path.join(ROOT, "tests", "host_emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(HERE, "emul.so")
+    src = os.path.join(HERE, "emul.cpp")
+    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "ec.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+    L = ctypes.CDLL(so)
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    L.emul_fp_op.argtypes = [i32, i32, vp, vp, vp, sz]
+    L.emul_ec_op.argtypes = [i32, i32, vp, vp, sz, i32]
+    L.emul_fp_mul_lazy.argtypes = [i32, vp, vp, vp, sz, i32, i32]
+    L.emul_constants.argtypes = [i32, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _limbs(v, n=14, bits=28):
+    return [(v >> (bits * i)) & ((1 << bits) - 1) if i < n - 1 else v >> (bits * i) for i in range(n)]
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_constant_tables(emul, curve):
+    """Every table in fp.cuh re-derived from p with Python integers."""
+    buf = np.zeros(64 + 16 * 14, np.uint32)
+    emul.emul_constants(curve, _p(buf))
+    p = RB.CURVES[curve]["p"]
+    val = lambda a: sum(int(x) << (28 * i) for i, x in enumerate(a))
+    assert val(buf[0:14]) == p
+    assert val(buf[14:28]) == (1 << 392) % p
+    assert val(buf[28:42]) == (1 << 400) % p
+    assert val(buf[42:56]) == (1 << 384) % p
+    assert int(buf[56]) == (-pow(p, -1, 1 << 28)) % (1 << 28)
+    assert int(buf[57]) == pow(p, -1, 1 << 28)
+    for k in range(16):
+        row = buf[64 + 14 * k: 64 + 14 * (k + 1)]
+        assert val(row) == (k + 1) * p                     # limb-dominant form is still exactly K p
+        assert all(int(x) >= (1 << 28) - 1 for x in row[:13])
+        assert all(int(x) < (1 << 32) for x in row)
+
+
+def _rand_fp(rng, n, p):
+    vals = [int.from_bytes(rng.bytes(48), "little") % p for _ in range(n)]
+    return vals
+
+
+def _pack(vals):
+    return np.frombuffer(b"".join(v.to_bytes(48, "little") for v in vals), np.uint8).copy()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_field_ops(emul, oracle, curve):
+    rng = np.random.default_rng(17 + curve)
+    p = RB.CURVES[curve]["p"]
+    n = 2048
+    va, vb = _rand_fp(rng, n, p), _rand_fp(rng, n, p)
+    va[:4] = [0, p - 1, 1, p - 1]
+    vb[:4] = [5, p - 1, p - 1, 0]
+    a, b = _pack(va), _pack(vb)
+    r = np.zeros_like(a)
+    for op, oop in ((0, oracle.FP_MUL), (1, oracle.FP_ADD), (2, oracle.FP_SUB), (3, oracle.FP_SQR)):
+        emul.emul_fp_op(curve, op, _p(a), _p(b), _p(r), n)
+        assert np.array_equal(r.reshape(-1, 48), oracle.fp_op(oop, a, b, curve)), (curve, op)
+    emul.emul_fp_op(curve, 4, _p(a[48:48 * 9]), _p(a[48:48 * 9]), _p(r), 8)
+    assert np.array_equal(r[:48 * 8].reshape(-1, 48), oracle.fp_op(oracle.FP_INV, a[48:48 * 9], None, curve))
+    emul.emul_fp_op(curve, 5, _p(a), _p(b), _p(r), n)
+    assert np.array_equal(r, a)
+
+
+@pytest.mark.parametrize("curve,k1,k2", [(0, 13, 13), (0, 10, 2), (1, 13, 13), (1, 8, 13)])
+def test_lazy_multiply_bound(emul, oracle, curve, k1, k2):
+    """(a + k1 p)(b + k2 p) stays below 2p after the Montgomery multiply: the bounds ec.cuh relies on."""
+    rng = np.random.default_rng(5)
+    p = RB.CURVES[curve]["p"]
+    n = 1024
+    va, vb = _rand_fp(rng, n, p), _rand_fp(rng, n, p)
+    va[0], vb[0] = p - 1, p - 1
+    a, b = _pack(va), _pack(vb)
+    r = np.zeros_like(a)
+    assert emul.emul_fp_mul_lazy(curve, _p(a), _p(b), _p(r), n, k1, k2) == 0
+    assert np.array_equal(r.reshape(-1, 48), oracle.fp_op(oracle.FP_MUL, a, b, curve))
+
+
+def _xyzz_from_aff(O, aff, curve):
+    one = np.frombuffer(O.constants(curve)["R"].to_bytes(48, "little"), np.uint8)
+    out = np.zeros((len(aff), 192), np.uint8)
+    out[:, :96] = aff[:, :96]
+    out[:, 96:144] = one
+    out[:, 144:] = one
+    return out
+
+
+def _jac_from_aff(O, aff, curve):
+    one = np.frombuffer(O.constants(curve)["R"].to_bytes(48, "little"), np.uint8)
+    out = np.zeros((len(aff), 144), np.uint8)
+    out[:, :96] = aff[:, :96]
+    out[:, 96:] = one
+    return out
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_curve_ops(emul, oracle, curve):
+    O = oracle
+    n = 64
+    A, B = O.gen_points(n, seed=5, curve=curve), O.gen_points(n, seed=9, curve=curve)
+    B[0] = A[0]                                   # P + P -> doubling branch
+    B[1] = O.aff_neg(A[1:2], curve)[0]            # P - P -> infinity
+    acc = _xyzz_from_aff(O, A, curve)
+    acc[2] = 0                                    # infinity + P
+    jac = _jac_from_aff(O, A, curve)
+    jac[2, 96:] = 0
+    b96 = np.ascontiguousarray(B[:, :96])
+    got = acc.copy()
+    emul.emul_ec_op(curve, 0, _p(got), _p(b96), n, 1)
+    assert np.array_equal(O.xyzz_to_affine(got, curve), O.jac_to_affine(O.jac_add_mixed(jac, B, curve), curve))
+    got9 = _xyzz_from_aff(O, A, curve)
+    emul.emul_ec_op(curve, 0, _p(got9), _p(b96), n, 9)
+    j = _jac_from_aff(O, A, curve)
+    for _ in range(9):
+        j = O.jac_add_mixed(j, B, curve)
+    assert np.array_equal(O.xyzz_to_affine(got9, curve), O.jac_to_affine(j, curve))
+    lhs, other = got9.copy(), got9.copy()
+    lhs[3] = 0
+    other[4] = 0
+    jl, jo = j.copy(), j.copy()
+    jl[3, 96:] = 0
+    jo[4, 96:] = 0
+    emul.emul_ec_op(curve, 1, _p(lhs), _p(other), n, 1)
+    assert np.array_equal(O.xyzz_to_affine(lhs, curve), O.jac_to_affine(O.jac_add(jl, jo, curve), curve))
+    d = got9.copy()
+    emul.emul_ec_op(curve, 2, _p(d), None, n, 23)
+    jd = j.copy()
+    for _ in range(23):
+        jd = O.jac_double(jd, curve)
+    assert np.array_equal(O.xyzz_to_affine(d, curve), O.jac_to_affine(jd, curve))
+    da = np.zeros((n, 192), np.uint8)
+    a96 = np.ascontiguousarray(A[:, :96])
+    emul.emul_ec_op(curve, 3, _p(da), _p(a96), n, 1)
+    assert np.array_equal(O.xyzz_to_affine(da, curve), O.jac_to_affine(O.jac_double(_jac_from_aff(O, A, curve), curve), curve))
