@@ -232,7 +232,7 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
         LaunchCold<C>::batch_normalize(ctx->stream, tmp, cnt, ctx->tables + first);
     }
     if (gen_n < n) {
-        uint64_t work = (uint64_t)(n - gen_n) * 6;
+        uint64_t work = (uint64_t)(n - gen_n) * AFF_VEC;
         k_replicate<<<cdiv(work, 256), 256, 0, ctx->stream>>>(ctx->tables, gen_n, n);
     }
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));

@@ -101,14 +101,14 @@ def test_smoke_entry():
     g.smoke()
 
 
-def _engine_result(M, O, eng, sc_np):
+def _engine_result(M, O, eng, sc_np, curve=0):
     import torch
     n = len(sc_np)
     sc = torch.from_numpy(np.ascontiguousarray(sc_np).reshape(-1)).cuda()
     out = torch.zeros(144, dtype=torch.uint8, device="cuda")
     eng.msm_device(sc.data_ptr(), n, out.data_ptr())
     eng.sync()
-    return O.jac_to_affine(out.cpu().numpy())[0]
+    return O.jac_to_affine(out.cpu().numpy(), curve)[0]
 
 
 @pytest.mark.parametrize("curve", [0, 1])
@@ -125,9 +125,15 @@ def test_random_msm_vs_oracle_window_plans(M, oracle, curve, cfg):
     sc[9] = sc[8]
     eng = M.Engine(curve, window_bits=cfg[0], tables=cfg[1])
     eng.set_bases(pts)
-    got = _engine_result(M, O, eng, sc)
+    got = _engine_result(M, O, eng, sc, curve)
+    info = eng.info()
     eng.close()
-    assert np.array_equal(got, O.jac_to_affine(O.ark_msm(pts, sc, curve), curve)[0])
+    want = O.jac_to_affine(O.ark_msm(pts, sc, curve), curve)[0]
+    if not np.array_equal(got, want):
+        naive = O.jac_to_affine(O.naive_msm(pts, sc, curve), curve)[0]
+        again = O.jac_to_affine(O.ark_msm(pts, sc, curve), curve)[0]
+        raise AssertionError(f"plan {info}: gpu==naive {np.array_equal(got, naive)}, oracle==naive {np.array_equal(want, naive)}, "
+                             f"oracle rerun equal {np.array_equal(want, again)}")
 
 
 @pytest.mark.parametrize("case", ["zeros", "ones", "r_minus_1", "all_equal", "top_bit", "sparse", "single_point"])
