@@ -29,8 +29,23 @@ struct xyzz_t { fp x, y, zz, zzz; };     // 224 bytes
 struct affine_abi_t { fp_abi x, y; };    // 96 bytes: arkworks (x, y), R = 2^384
 struct xyzz_abi_t { fp_abi x, y, zz, zzz; };
 
+// EC_MUL_BY_CALL (defined by the hot translation units): field multiply / square become real calls with operands and
+// result in registers (by-value ABI).  One copy of each body per kernel instead of ten inlined per mixed add keeps
+// the accumulate loop inside the instruction cache (ncu: stall_no_instruction 2.5 cycles per issue when inlined).
+#if defined(__CUDACC__) && defined(EC_MUL_BY_CALL)
+template <class C> __device__ __noinline__ fp fp_mul_call(fp a, fp b) { fp r; Fp<C>::mul(r, a, b); return r; }
+template <class C> __device__ __noinline__ fp fp_sqr_call(fp a) { fp r; Fp<C>::sqr(r, a); return r; }
+#endif
+
 template <class C> struct Ec {
     typedef Fp<C> F;
+#if defined(__CUDACC__) && defined(EC_MUL_BY_CALL)
+    __device__ __forceinline__ static void M(fp &r, const fp &a, const fp &b) { r = fp_mul_call<C>(a, b); }
+    __device__ __forceinline__ static void S(fp &r, const fp &a) { r = fp_sqr_call<C>(a); }
+#else
+    FP_HD static void M(fp &r, const fp &a, const fp &b) { F::mul(r, a, b); }
+    FP_HD static void S(fp &r, const fp &a) { F::sqr(r, a); }
+#endif
 
     FP_HD static void set_inf(xyzz_t &a) {
         F::set_zero(a.x); F::set_zero(a.y); F::set_zero(a.zz); F::set_zero(a.zzz);
@@ -43,18 +58,18 @@ template <class C> struct Ec {
     FP_HD static void dbl_affine(xyzz_t &r, const fp &x, const fp &y) {
         fp u, v, w, s, m, t;
         F::add(u, y, y);                  // U = 2Y                    4
-        F::sqr(v, u);                     // V = U^2                   2
-        F::mul(w, u, v);                  // W = U*V                   2
-        F::mul(s, x, v);                  // S = X*V                   2
-        F::sqr(t, x);
+        S(v, u);                     // V = U^2                   2
+        M(w, u, v);                  // W = U*V                   2
+        M(s, x, v);                  // S = X*V                   2
+        S(t, x);
         F::add(m, t, t);
         F::add(m, m, t);                  // M = 3X^2                  6
-        F::sqr(r.x, m);
+        S(r.x, m);
         F::add(t, s, s);                  // 2S                        4
         F::template sub<5>(r.x, r.x, t);  // X3 = M^2 - 2S             7
         F::template sub<8>(t, s, r.x);    // S - X3                    10
-        F::mul(t, m, t);                  // 6 * 10
-        F::mul(s, w, y);
+        M(t, m, t);                  // 6 * 10
+        M(s, w, y);
         F::template sub<3>(r.y, t, s);    // Y3                        5
         r.zz = v;
         r.zzz = w;
@@ -63,84 +78,84 @@ template <class C> struct Ec {
     FP_HD static void dbl(xyzz_t &a) {
         fp u, v, w, s, m, t;
         F::add(u, a.y, a.y);              // U = 2Y1                   10
-        F::sqr(v, u);                     // 100
-        F::mul(w, u, v);                  // 10 * 2
-        F::mul(s, a.x, v);                // 10 * 2
-        F::sqr(t, a.x);                   // 100
+        S(v, u);                     // 100
+        M(w, u, v);                  // 10 * 2
+        M(s, a.x, v);                // 10 * 2
+        S(t, a.x);                   // 100
         F::add(m, t, t);
         F::add(m, m, t);                  // M = 3 X1^2                6
         fp x3, y3;
-        F::sqr(x3, m);                    // 36
+        S(x3, m);                    // 36
         F::add(t, s, s);                  //                           4
         F::template sub<5>(x3, x3, t);    // X3                        7
         F::template sub<8>(t, s, x3);     // S - X3                    10
-        F::mul(t, m, t);                  // 60
-        F::mul(y3, w, a.y);               // 2 * 5
+        M(t, m, t);                  // 60
+        M(y3, w, a.y);               // 2 * 5
         F::template sub<3>(a.y, t, y3);   // Y3                        5
         a.x = x3;
-        F::mul(a.zz, v, a.zz);
-        F::mul(a.zzz, w, a.zzz);
+        M(a.zz, v, a.zz);
+        M(a.zzz, w, a.zzz);
     }
     // acc += (x2, y2) with (x2, y2) affine, < 2p, not infinity  (madd-2008-s: 8M + 2S)
     FP_HD static void madd(xyzz_t &acc, const fp &x2, const fp &y2) {
         if (is_inf(acc)) { from_affine(acc, x2, y2); return; }
         fp p, r, pp, ppp, q, t;
-        F::mul(p, x2, acc.zz);                  // U2                       2
-        F::mul(r, y2, acc.zzz);                 // S2                       2
+        M(p, x2, acc.zz);                  // U2                       2
+        M(r, y2, acc.zzz);                 // S2                       2
         F::template sub<11>(p, p, acc.x);       // P = U2 - X1              13
         F::template sub<6>(r, r, acc.y);        // R = S2 - Y1              8
         if (F::is_zero(p)) {
             if (F::is_zero(r)) dbl_affine(acc, x2, y2); else set_inf(acc);
             return;
         }
-        F::sqr(pp, p);                          // 13 * 13
-        F::mul(ppp, p, pp);                     // 13 * 2
-        F::mul(q, acc.x, pp);                   // 10 * 2
-        F::sqr(t, r);                           // 8 * 8
+        S(pp, p);                          // 13 * 13
+        M(ppp, p, pp);                     // 13 * 2
+        M(q, acc.x, pp);                   // 10 * 2
+        S(t, r);                           // 8 * 8
         F::template sub<3>(t, t, ppp);          // R^2 - PPP                5
         fp q2;
         F::add(q2, q, q);                       // 2Q                       4
         F::template sub<5>(t, t, q2);           // X3                       10
         F::template sub<11>(q, q, t);           // Q - X3                   13
-        F::mul(q, r, q);                        // 8 * 13
-        F::mul(r, acc.y, ppp);                  // 5 * 2
+        M(q, r, q);                        // 8 * 13
+        M(r, acc.y, ppp);                  // 5 * 2
         F::template sub<3>(acc.y, q, r);        // Y3                       5
         acc.x = t;
-        F::mul(acc.zz, acc.zz, pp);
-        F::mul(acc.zzz, acc.zzz, ppp);
+        M(acc.zz, acc.zz, pp);
+        M(acc.zzz, acc.zzz, ppp);
     }
     // a += b  (add-2008-s: 12M + 2S)
     FP_HD static void add(xyzz_t &a, const xyzz_t &b) {
         if (is_inf(b)) return;
         if (is_inf(a)) { a = b; return; }
         fp u1, u2, s1, s2, pp, ppp, q, t;
-        F::mul(u1, a.x, b.zz);                  // 10 * 2
-        F::mul(u2, b.x, a.zz);
-        F::mul(s1, a.y, b.zzz);                 // 5 * 2
-        F::mul(s2, b.y, a.zzz);
+        M(u1, a.x, b.zz);                  // 10 * 2
+        M(u2, b.x, a.zz);
+        M(s1, a.y, b.zzz);                 // 5 * 2
+        M(s2, b.y, a.zzz);
         F::template sub<3>(u2, u2, u1);         // P                        5
         F::template sub<3>(s2, s2, s1);         // R                        5
         if (F::is_zero(u2)) {
             if (F::is_zero(s2)) dbl(a); else set_inf(a);
             return;
         }
-        F::sqr(pp, u2);                         // 25
-        F::mul(ppp, u2, pp);
-        F::mul(q, u1, pp);
-        F::sqr(t, s2);
+        S(pp, u2);                         // 25
+        M(ppp, u2, pp);
+        M(q, u1, pp);
+        S(t, s2);
         F::template sub<3>(t, t, ppp);          //                          5
         fp q2;
         F::add(q2, q, q);                       //                          4
         F::template sub<5>(t, t, q2);           // X3                       10
         F::template sub<11>(q, q, t);           // Q - X3                   13
-        F::mul(q, s2, q);                       // 5 * 13
-        F::mul(s1, s1, ppp);
+        M(q, s2, q);                       // 5 * 13
+        M(s1, s1, ppp);
         F::template sub<3>(a.y, q, s1);         // Y3                       5
         a.x = t;
-        F::mul(a.zz, a.zz, b.zz);
-        F::mul(a.zz, a.zz, pp);
-        F::mul(a.zzz, a.zzz, b.zzz);
-        F::mul(a.zzz, a.zzz, ppp);
+        M(a.zz, a.zz, b.zz);
+        M(a.zz, a.zz, pp);
+        M(a.zzz, a.zzz, b.zzz);
+        M(a.zzz, a.zzz, ppp);
     }
     // canonical affine (x, y) of a finite XYZZ point:  x = X * ZZ^2 / ZZZ^2,  y = Y / ZZZ   (one inversion)
     FP_HD static void to_affine(fp &x, fp &y, const xyzz_t &a) {

@@ -65,9 +65,7 @@ __global__ void __launch_bounds__(128) k_block_sum(const xyzz_t *__restrict__ in
 // a10: finalize (one block, one warp per term).  Per folded window f the host hands a list of terms, each an array of
 // <= 32 points:   kind 0: 2^shift * sum(arr)        kind 1: 2^shift * sum_k k * arr[k]
 // window value = sum of its terms; result = Horner over windows with c doublings; then either the XYZZ value is
-// stored (partial result of one GPU) or it is exported as an arkworks G1Projective: Jacobian (X*ZZ, Y*ZZZ, ZZ) -- with
-// ZZ = z^2, ZZZ = z^3 that is (x z^4, y z^6, z^2), a representative of (x, y) that needs no inversion (the harness
-// compares projectively / normalises on its side) -- or (1, 1, 0) for infinity.  All limbs canonical (< p).
+// stored (partial result of one GPU) or it is exported as an arkworks G1Projective (export_jacobian).
 #define FIN_WARPS 8
 template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
     // tree sum of the 32 lanes' points through shared memory; result in lane 0
@@ -80,8 +78,21 @@ template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
     }
     __syncwarp();
 }
+// XYZZ -> arkworks G1Projective (Jacobian x, y, z; 3 x 6 x u64 Montgomery R = 2^384): the canonical affine point with
+// z = 1, or the arkworks zero (1, 1, 0).  One inversion (~0.1 ms on one thread) buys a byte-deterministic result: the
+// XYZZ representative depends on the order the scatter's atomics filled the buckets, the normalised point does not.
+template <class C> __device__ void export_jacobian(const xyzz_t &total, uint32_t *out_jac) {
+    fp x, y, z;
+    Fp<C>::set_one(z);
+    if (Ec<C>::is_inf(total)) { Fp<C>::set_one(x); Fp<C>::set_one(y); Fp<C>::set_zero(z); }
+    else Ec<C>::to_affine_ni(x, y, total);
+    fp_abi ox, oy, oz;
+    Ec<C>::to_abi_ni(ox, x); Ec<C>::to_abi_ni(oy, y); Ec<C>::to_abi_ni(oz, z);
+#pragma unroll
+    for (int i = 0; i < 12; i++) { out_jac[i] = ox.w[i]; out_jac[12 + i] = oy.w[i]; out_jac[24 + i] = oz.w[i]; }
+}
 template <class C>
-__global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_t *__restrict__ out_xyzz, uint32_t *__restrict__ out_jac, int extra_n, const xyzz_t *__restrict__ extra) {
+__global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_t *__restrict__ out_xyzz, uint32_t *__restrict__ out_jac) {
     __shared__ xyzz_t sh[FIN_WARPS][16];
     __shared__ xyzz_t slot[FIN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -123,33 +134,20 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_
         }
         __syncthreads();
     }
-    if (warp != 0) return;
-    // optional: add further partial results (other GPUs' XYZZ partials, lane-parallel)
-    if (extra_n > 0) {
-        xyzz_t v;
-        Ec<C>::set_inf(v);
-        for (int k = lane; k < extra_n; k += 32) { xyzz_t t; load_xyzz(t, extra + k); Ec<C>::add_ni(v, t); }
-        warp_sum<C>(v, sh[0]);
-        if (lane == 0) Ec<C>::add_ni(total, v);
-    }
-    if (lane == 0) {
-        if (out_xyzz) {
-            store_xyzz(out_xyzz, total);
-        }
-        if (out_jac) {
-            fp x, y, z;
-            if (Ec<C>::is_inf(total)) { Fp<C>::set_one(x); Fp<C>::set_one(y); Fp<C>::set_zero(z); }
-            else {
-                Ec<C>::mul_ni(x, total.x, total.zz);
-                Ec<C>::mul_ni(y, total.y, total.zzz);
-                z = total.zz;
-            }
-            fp_abi ox, oy, oz;
-            Ec<C>::to_abi_ni(ox, x); Ec<C>::to_abi_ni(oy, y); Ec<C>::to_abi_ni(oz, z);
-#pragma unroll
-            for (int i = 0; i < 12; i++) { out_jac[i] = ox.w[i]; out_jac[12 + i] = oy.w[i]; out_jac[24 + i] = oz.w[i]; }
-        }
-    }
+    if (warp != 0 || lane != 0) return;
+    if (out_xyzz) store_xyzz(out_xyzz, total);
+    if (out_jac) export_jacobian<C>(total, out_jac);
+}
+// a10 (multi-GPU): sum `count` partial results (one XYZZ record per GPU, gathered over NVLink) and export.  One warp.
+template <class C>
+__global__ void __launch_bounds__(32) k_combine(const xyzz_t *__restrict__ parts, int count, uint32_t *__restrict__ out_jac) {
+    __shared__ xyzz_t sh[16];
+    const int lane = threadIdx.x;
+    xyzz_t v;
+    Ec<C>::set_inf(v);
+    for (int k = lane; k < count; k += 32) { xyzz_t t; load_xyzz(t, parts + k); Ec<C>::add_ni(v, t); }
+    warp_sum<C>(v, sh);
+    if (lane == 0) export_jacobian<C>(v, out_jac);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
 // slots ([stage][16-byte chunk][thread]: conflict-free) while the current mixed add (~3000 integer instructions)
 // runs, so the random gather latency is hidden by one stage of prefetch.  Results go to res[piece].
 template <class C>
-__global__ void __launch_bounds__(ACC_TPB) k_accumulate(const affine_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+__global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const affine_t *__restrict__ tables, const uint32_t *__restrict__ refs,
                                                         const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
                                                         const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
                                                         xyzz_t *__restrict__ res) {

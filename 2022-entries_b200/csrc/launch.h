@@ -22,7 +22,8 @@ template <class C> struct LaunchCold {
     // n_out threads in blocks of `block` (n_out % block == 0); outT gets one entry per block
     static void reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT);
     static void block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out);
-    static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, int extra_n, const xyzz_t *extra);
+    static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac);
+    static void combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac);
     static void double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp);
     static void batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst);
     static void gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp);

@@ -13,8 +13,11 @@ template <class C> void LaunchCold<C>::block_sum(cudaStream_t st, const xyzz_t *
     k_block_sum<C><<<ngroups, group < 128 ? group : 128, 0, st>>>(in, group, out);
 }
 template <class C>
-void LaunchCold<C>::finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, int extra_n, const xyzz_t *extra) {
-    k_finalize<C><<<1, 32 * 8, 0, st>>>(a, out_xyzz, out_jac, extra_n, extra);
+void LaunchCold<C>::finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac) {
+    k_finalize<C><<<1, 32 * 8, 0, st>>>(a, out_xyzz, out_jac);
+}
+template <class C> void LaunchCold<C>::combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac) {
+    k_combine<C><<<1, 32, 0, st>>>(parts, count, out_jac);
 }
 template <class C> void LaunchCold<C>::double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp) {
     k_double_n<C><<<cdiv(n, 128), 128, 0, st>>>(src, n, k, tmp);

@@ -319,7 +319,7 @@ template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_de
         launches++;
     }
     cudaEventRecord(ctx->ev[5], st);
-    LaunchCold<C>::finalize(st, ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac, 0, nullptr);
+    LaunchCold<C>::finalize(st, ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac);
     launches++;
     cudaEventRecord(ctx->ev[6], st);
     ctx->launches = launches;
@@ -471,11 +471,8 @@ int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64
 int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!xyzz_dev || count < 1 || !out_jacobian_dev) return ctx->fail(-1, "b200msm_combine_device: bad argument");
-    fin_args_t fin;
-    memset(&fin, 0, sizeof(fin));
-    fin.F = 0; fin.c = 1;
-    if (ctx->curve == 0) LaunchCold<Bls12_377>::finalize(ctx->stream, fin, nullptr, (uint32_t *)out_jacobian_dev, count, (const xyzz_t *)xyzz_dev);
-    else LaunchCold<Bls12_381>::finalize(ctx->stream, fin, nullptr, (uint32_t *)out_jacobian_dev, count, (const xyzz_t *)xyzz_dev);
+    if (ctx->curve == 0) LaunchCold<Bls12_377>::combine(ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev);
+    else LaunchCold<Bls12_381>::combine(ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev);
     CK(cudaGetLastError());
     return 0;
 }
