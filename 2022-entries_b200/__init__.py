@@ -69,6 +69,7 @@ def lib():
     L.b200msm_get_stage_ms_sum.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]
     L.b200msm_test_fp_op.argtypes = [i32, i32, vp, vp, vp, u64]
     L.b200msm_test_ec_op.argtypes = [i32, i32, vp, vp, u64, i32]
+    L.b200msm_test_grp_op.argtypes = [i32, i32, vp, vp, vp, u64, i32]
     L.mult_pippenger_init.argtypes = [ctypes.POINTER(_FfiContext), vp, sz, sz]
     L.mult_pippenger_init.restype = _RustError
     L.mult_pippenger_inf.argtypes = [ctypes.POINTER(_FfiContext), vp, vp, sz, sz, vp, sz]
@@ -91,7 +92,7 @@ EXPORTED_SYMBOLS = [
     "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
     "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
-    "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "mult_pippenger_init", "mult_pippenger_inf",
+    "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "b200msm_test_grp_op", "mult_pippenger_init", "mult_pippenger_inf",
     "mult_pippenger_free", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
 ]
 
@@ -322,3 +323,14 @@ def test_ec_op(curve, op, acc, other=None, reps=1):
     if rc != 0:
         raise MsmError(f"b200msm_test_ec_op: {rc}: {lib().b200msm_last_error(None).decode()}")
     return acc.reshape(-1, XYZZ_ABI_BYTES)
+
+
+def test_grp_op(curve, op, a, b, reps=1):
+    """a, b: uint8[n, 96] arkworks (x, y); returns uint8[n, 104] G1Affine records."""
+    a, b = _as_u8(a, 96, "a"), _as_u8(b, 96, "b")
+    n = a.size // 96
+    out = np.zeros((n, AFFINE_BYTES), np.uint8)
+    rc = lib().b200msm_test_grp_op(curve, op, _ptr(a), _ptr(b), _ptr(out), n, reps)
+    if rc != 0:
+        raise MsmError(f"b200msm_test_grp_op: {rc}: {lib().b200msm_last_error(None).decode()}")
+    return out

@@ -72,6 +72,31 @@ struct Bls12_377 {
         constexpr uint32_t v[8] = {0x00000001u, 0x0a118000u, 0xd0000001u, 0x59aa76feu, 0x5c37b001u, 0x60b44d1eu, 0x9a2ca556u, 0x12ab655eu};
         return v[i];
     }
+    // Twisted-Edwards model of G1 with a = -1 (te.cuh): -x^2 + y^2 = 1 + d x^2 y^2.  All in Montgomery form (2^392);
+    // tests/test_host_emul.py re-derives them from p (s = 1/sqrt(3), Montgomery A = -3s, B = s, a1 = (A+2)/B,
+    // d1 = (A-2)/B, f = sqrt(-a1), d = -d1/a1 -- the parameters arkworks lists for this curve,
+    // P1B/nickray/driver/bls12-377/src/curves/g1.rs:52-113).
+    static constexpr bool HAS_TE = true;
+    FP_HD static constexpr uint32_t te_k(int i) {    // 2 d
+        constexpr uint32_t v[14] = {0x706c521u, 0xdf4444au, 0x8fa7e68u, 0x371b2aau, 0xdd6cd3du, 0xebe579eu, 0x3577a6au, 0x1d3f1c6u, 0x2ada318u, 0x2a73d9du, 0x7da6ef5u, 0xce09495u, 0xfed4ab8u, 0x0001813u};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t te_f(int i) {    // sqrt(-a1): x scaling that makes a = -1
+        constexpr uint32_t v[14] = {0x605e344u, 0x9db8eadu, 0xc7a99c9u, 0x53cf352u, 0x6254f3bu, 0x07ad145u, 0x769ac1au, 0xeb261abu, 0xa5ececdu, 0x625c845u, 0x568b26eu, 0x37d10bau, 0x84097bau, 0x0000867u};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t te_s(int i) {    // 1 / sqrt(3)
+        constexpr uint32_t v[14] = {0x1a0a113u, 0xb0dad83u, 0xc8df2c0u, 0xc9ee451u, 0x1935a6eu, 0x6425e1bu, 0xacf94dfu, 0x9d801ddu, 0x14590dbu, 0xad64a0cu, 0x2a17c35u, 0x6b6b819u, 0x0112a8cu, 0x0000fa6u};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t te_s3(int i) {   // sqrt(3) = 1 / s
+        constexpr uint32_t v[14] = {0x4e1e338u, 0x09d0889u, 0x5a9d7bdu, 0x00869f5u, 0xcb9f841u, 0xfcb79bcu, 0x14fcb3bu, 0xd78b460u, 0x9add89fu, 0x66e4a72u, 0xcdeb434u, 0x3157be7u, 0x5ed67e0u, 0x000140eu};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t te_cy(int i) {   // f / s
+        constexpr uint32_t v[14] = {0xcfd10d5u, 0x9457a38u, 0x383e475u, 0x7e96cb8u, 0x388e8d9u, 0xd00b5abu, 0xd32ebe1u, 0x0c15e03u, 0x5ac3c51u, 0xa270ad8u, 0xe68d2ebu, 0xbe54908u, 0x8029609u, 0x00001c4u};
+        return v[i];
+    }
 };
 
 struct Bls12_381 {
@@ -99,6 +124,12 @@ struct Bls12_381 {
                                     0x7052574u, 0x7ce5853u, 0x56ec6d7u, 0x71a97a2u, 0xe4935c0u, 0xec3fa80u, 0x0015f65u};
         return v[i];
     }
+    static constexpr bool HAS_TE = false;            // cofactor not divisible by 4: no Montgomery / twisted-Edwards model
+    FP_HD static constexpr uint32_t te_k(int) { return 0; }
+    FP_HD static constexpr uint32_t te_f(int) { return 0; }
+    FP_HD static constexpr uint32_t te_s(int) { return 0; }
+    FP_HD static constexpr uint32_t te_s3(int) { return 0; }
+    FP_HD static constexpr uint32_t te_cy(int) { return 0; }
     FP_HD static constexpr uint32_t r(int i) {
         constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
         return v[i];

@@ -1,0 +1,145 @@
+// grp.cuh -- the bucket coordinate system of a curve, as the kernels see it.  Grp<C> is
+//   GrpTe<C>    twisted-Edwards extended coordinates, 7 M unified mixed add, 144-byte packed table entries (BLS12-377)
+//   GrpXyzz<C>  short-Weierstrass XYZZ, 8 M + 2 S mixed add with infinity / doubling cases, 112-byte entries (BLS12-381)
+// A bucket is four field elements in both (struct xyzz_t).  Base tables are built in short-Weierstrass affine form
+// (doubling chains + batched normalisation, kernels_cold.cuh) and converted to entries chunk by chunk.
+#pragma once
+#include "te.cuh"
+
+namespace b200msm {
+
+#define GRP_BATCH 16      // points per thread in the entry conversion (one inversion per batch)
+
+template <class C> struct GrpXyzz {
+    typedef Fp<C> F;
+    typedef affine_t entry_t;
+    static constexpr int ENTRY_VEC = sizeof(affine_t) / 16;       // 7
+    FP_HD static void set_inf(xyzz_t &a) { Ec<C>::set_inf(a); }
+#if defined(__CUDACC__)
+    // acc += entry, the entry staged as ENTRY_VEC 16-byte chunks `stride` uint4 apart
+    __device__ __forceinline__ static void madd_staged(xyzz_t &acc, const uint4 *st, int stride, bool negate) {
+        affine_t pt;
+        uint4 *t = reinterpret_cast<uint4 *>(&pt);
+#pragma unroll
+        for (int k = 0; k < ENTRY_VEC; k++) t[k] = st[k * stride];
+        if (negate) F::template neg<2>(pt.y, pt.y);
+        Ec<C>::madd(acc, pt.x, pt.y);
+    }
+    __device__ __noinline__ static void add_ni(xyzz_t &a, const xyzz_t &b) { Ec<C>::add(a, b); }
+    __device__ __noinline__ static void dbl_ni(xyzz_t &a) { Ec<C>::dbl(a); }
+    __device__ static bool to_sw_affine(fp &x, fp &y, const xyzz_t &a) {
+        if (Ec<C>::is_inf(a)) return false;
+        Ec<C>::to_affine_ni(x, y, a);
+        return true;
+    }
+    // thread t converts src[t*GRP_BATCH ...] (short-Weierstrass affine, canonical) to entries: a copy here
+    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t) {
+        for (uint32_t k = 0; k < GRP_BATCH; k++) {
+            const uint32_t i = t * GRP_BATCH + k;
+            if (i >= n) return;
+            const uint4 *s = reinterpret_cast<const uint4 *>(src + i);
+            uint4 *d = reinterpret_cast<uint4 *>(dst + i);
+#pragma unroll
+            for (int v = 0; v < ENTRY_VEC; v++) d[v] = s[v];
+        }
+    }
+    __device__ static void entry_to_sw(fp &x, fp &y, const entry_t &e) { x = e.x; y = e.y; }
+#endif
+};
+
+template <class C> struct GrpTe {
+    typedef Fp<C> F;
+    typedef te_entry_t entry_t;
+    static constexpr int ENTRY_VEC = sizeof(te_entry_t) / 16;     // 9
+    FP_HD static void set_inf(xyzz_t &a) { Te<C>::set_inf(a); }
+#if defined(__CUDACC__)
+    __device__ __forceinline__ static void madd_staged(xyzz_t &acc, const uint4 *st, int stride, bool negate) {
+        te_entry_t e;
+        uint4 *t = reinterpret_cast<uint4 *>(&e);
+#pragma unroll
+        for (int k = 0; k < ENTRY_VEC; k++) t[k] = st[k * stride];
+        te_pre_t q;
+        Te<C>::unpack(q, e);
+        if (negate) Te<C>::negate(q);
+        Te<C>::madd(acc, q);
+    }
+    __device__ __noinline__ static void add_ni(xyzz_t &a, const xyzz_t &b) { Te<C>::add(a, b); }
+    __device__ __noinline__ static void dbl_ni(xyzz_t &a) { Te<C>::dbl(a); }
+    __device__ __noinline__ static bool to_sw_affine(fp &x, fp &y, const xyzz_t &a) {
+        if (Te<C>::is_inf(a)) return false;
+        fp zmy, zpy, den, inv, t, one, c3, cy;
+        F::template sub<3>(zmy, a.zz, a.y);
+        F::add(zpy, a.zz, a.y);
+        Ec<C>::mul_ni(den, a.x, zmy);
+        Ec<C>::inv_ni(inv, den);
+        Ec<C>::mul_ni(t, zpy, inv);
+        Te<C>::load_const(c3, 3);
+        Te<C>::load_const(cy, 4);
+        F::set_one(one);
+        Ec<C>::mul_ni(x, t, a.x);
+        Ec<C>::mul_ni(x, x, c3);
+        F::template sub<2>(x, x, one);
+        Ec<C>::mul_ni(y, t, a.zz);
+        Ec<C>::mul_ni(y, y, cy);
+        Ec<C>::mul_ni(x, x, one);                 // canonical representatives: x * R / R, then < p
+        Ec<C>::mul_ni(y, y, one);
+        F::csub_p(x);
+        F::csub_p(y);
+        return true;
+    }
+    // Montgomery's trick over GRP_BATCH points: one inversion per thread.  A zero denominator (y = 0 or
+    // s (x + 1) = -1: only for points outside G1, or the (0, 0) placeholder of a base flagged infinity, which the digit
+    // kernel never references) is replaced by 1 so that it cannot poison its batch.
+    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t) {
+        const uint32_t base = t * GRP_BATCH;
+        if (base >= n) return;
+        const uint32_t cnt = n - base < GRP_BATCH ? n - base : GRP_BATCH;
+        fp prefix[GRP_BATCH];
+        fp acc;
+        F::set_one(acc);
+        for (uint32_t k = 0; k < cnt; k++) {
+            affine_t a;
+            load_affine_plain(a, src + base + k);
+            fp nu, nv, dv, den;
+            Te<C>::map_prepare(nu, nv, dv, den, a.x, a.y);
+            if (F::is_zero(den)) F::set_one(den);
+            prefix[k] = acc;
+            Ec<C>::mul_ni(acc, acc, den);
+        }
+        fp inv;
+        Ec<C>::inv_ni(inv, acc);
+        for (uint32_t k = cnt; k-- > 0;) {
+            affine_t a;
+            load_affine_plain(a, src + base + k);
+            fp nu, nv, dv, den, i1;
+            Te<C>::map_prepare(nu, nv, dv, den, a.x, a.y);       // recomputed: cheaper than keeping 4 x GRP_BATCH values
+            if (F::is_zero(den)) F::set_one(den);
+            Ec<C>::mul_ni(i1, inv, prefix[k]);
+            Ec<C>::mul_ni(inv, inv, den);
+            te_entry_t e;
+            Te<C>::map_finish(e, nu, nv, dv, a.y, i1);
+            uint4 *d = reinterpret_cast<uint4 *>(dst + base + k);
+            const uint4 *s = reinterpret_cast<const uint4 *>(&e);
+#pragma unroll
+            for (int v = 0; v < ENTRY_VEC; v++) d[v] = s[v];
+        }
+    }
+    __device__ static void entry_to_sw(fp &x, fp &y, const entry_t &e) {
+        xyzz_t a;
+        Te<C>::entry_to_point(a, e);
+        if (!to_sw_affine(x, y, a)) { F::set_zero(x); F::set_zero(y); }
+    }
+    __device__ static void load_affine_plain(affine_t &d, const affine_t *src) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(src);
+        uint4 *t = reinterpret_cast<uint4 *>(&d);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(affine_t) / 16); i++) t[i] = s[i];
+    }
+#endif
+};
+
+template <class C, bool TE = C::HAS_TE> struct GrpSel { typedef GrpXyzz<C> type; };
+template <class C> struct GrpSel<C, true> { typedef GrpTe<C> type; };
+template <class C> using Grp = typename GrpSel<C>::type;
+
+}  // namespace b200msm

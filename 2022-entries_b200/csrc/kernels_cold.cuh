@@ -24,7 +24,7 @@ template <class C> __device__ __forceinline__ void block_tree_sum(xyzz_t &v, xyz
         __syncthreads();
         if (threadIdx.x >= o && threadIdx.x < 2 * o) store_xyzz(sh + threadIdx.x - o, v);
         __syncthreads();
-        if (threadIdx.x < o) { xyzz_t t; load_xyzz(t, sh + threadIdx.x); Ec<C>::add_ni(v, t); }
+        if (threadIdx.x < o) { xyzz_t t; load_xyzz(t, sh + threadIdx.x); Grp<C>::add_ni(v, t); }
     }
 }
 template <class C, bool INDIRECT>
@@ -33,17 +33,17 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
     __shared__ xyzz_t sh[64];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the outputs exactly
     xyzz_t run, tot, b;
-    Ec<C>::set_inf(run);
-    Ec<C>::set_inf(tot);
+    Grp<C>::set_inf(run);
+    Grp<C>::set_inf(tot);
     for (uint32_t jj = m; jj-- > 0;) {
         uint32_t k = t * m + jj;
-        if (jj + 1 < m) Ec<C>::add_ni(tot, run);                   // after the loop: tot = sum_j j * B_j
+        if (jj + 1 < m) Grp<C>::add_ni(tot, run);                   // after the loop: tot = sum_j j * B_j
         if (INDIRECT) {
             uint32_t p0 = piece_off[k], p1 = piece_off[k + 1];
-            for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, in + q); Ec<C>::add_ni(run, b); }
+            for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, in + q); Grp<C>::add_ni(run, b); }
         } else {
             load_xyzz(b, in + k);
-            Ec<C>::add_ni(run, b);
+            Grp<C>::add_ni(run, b);
         }
     }
     store_xyzz(outS + t, run);
@@ -55,8 +55,8 @@ template <class C>
 __global__ void __launch_bounds__(128) k_block_sum(const xyzz_t *__restrict__ in, uint32_t group, xyzz_t *__restrict__ out) {
     __shared__ xyzz_t sh[64];
     xyzz_t v, b;
-    Ec<C>::set_inf(v);
-    for (uint32_t k = threadIdx.x; k < group; k += blockDim.x) { load_xyzz(b, in + (size_t)blockIdx.x * group + k); Ec<C>::add_ni(v, b); }
+    Grp<C>::set_inf(v);
+    for (uint32_t k = threadIdx.x; k < group; k += blockDim.x) { load_xyzz(b, in + (size_t)blockIdx.x * group + k); Grp<C>::add_ni(v, b); }
     block_tree_sum<C>(v, sh);
     if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, v);
 }
@@ -74,7 +74,7 @@ template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
         __syncwarp();
         if (lane >= o && lane < 2 * o) store_xyzz(sh + lane - o, v);
         __syncwarp();
-        if (lane < o) { xyzz_t t; load_xyzz(t, sh + lane); Ec<C>::add_ni(v, t); }
+        if (lane < o) { xyzz_t t; load_xyzz(t, sh + lane); Grp<C>::add_ni(v, t); }
     }
     __syncwarp();
 }
@@ -84,8 +84,7 @@ template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
 template <class C> __device__ void export_jacobian(const xyzz_t &total, uint32_t *out_jac) {
     fp x, y, z;
     Fp<C>::set_one(z);
-    if (Ec<C>::is_inf(total)) { Fp<C>::set_one(x); Fp<C>::set_one(y); Fp<C>::set_zero(z); }
-    else Ec<C>::to_affine_ni(x, y, total);
+    if (!Grp<C>::to_sw_affine(x, y, total)) { Fp<C>::set_one(x); Fp<C>::set_one(y); Fp<C>::set_zero(z); }
     fp_abi ox, oy, oz;
     Ec<C>::to_abi_ni(ox, x); Ec<C>::to_abi_ni(oy, y); Ec<C>::to_abi_ni(oz, z);
 #pragma unroll
@@ -97,39 +96,39 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_
     __shared__ xyzz_t slot[FIN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     xyzz_t total;                       // meaningful in thread 0
-    Ec<C>::set_inf(total);
+    Grp<C>::set_inf(total);
     for (int f = a.F - 1; f >= 0; f--) {
         xyzz_t part;                    // this warp's share of the window value (lane 0)
-        Ec<C>::set_inf(part);
+        Grp<C>::set_inf(part);
         for (int ti = warp; ti < a.nterms; ti += FIN_WARPS) {
             const fin_term_t &tm = a.term[ti];
             xyzz_t v;
-            Ec<C>::set_inf(v);
+            Grp<C>::set_inf(v);
             if ((uint32_t)lane < tm.n) {
                 load_xyzz(v, tm.arr + (size_t)f * tm.stride_f + lane);
                 if (tm.kind == 1) {         // lane * v by double-and-add over 5 bits
                     xyzz_t r;
-                    Ec<C>::set_inf(r);
-                    for (int b = 4; b >= 0; b--) { Ec<C>::dbl_ni(r); if ((lane >> b) & 1) Ec<C>::add_ni(r, v); }
+                    Grp<C>::set_inf(r);
+                    for (int b = 4; b >= 0; b--) { Grp<C>::dbl_ni(r); if ((lane >> b) & 1) Grp<C>::add_ni(r, v); }
                     v = r;
                 }
             }
             warp_sum<C>(v, sh[warp]);
             if (lane == 0) {
-                for (uint32_t s = 0; s < tm.shift; s++) Ec<C>::dbl_ni(v);
-                Ec<C>::add_ni(part, v);
+                for (uint32_t s = 0; s < tm.shift; s++) Grp<C>::dbl_ni(v);
+                Grp<C>::add_ni(part, v);
             }
         }
         if (lane == 0) store_xyzz(&slot[warp], part);
         __syncthreads();
         if (warp == 0) {
             xyzz_t v;
-            Ec<C>::set_inf(v);
+            Grp<C>::set_inf(v);
             if (lane < FIN_WARPS) load_xyzz(v, &slot[lane]);
             warp_sum<C>(v, sh[0]);
             if (lane == 0) {
-                if (f != a.F - 1) for (int s = 0; s < a.c; s++) Ec<C>::dbl_ni(total);
-                Ec<C>::add_ni(total, v);
+                if (f != a.F - 1) for (int s = 0; s < a.c; s++) Grp<C>::dbl_ni(total);
+                Grp<C>::add_ni(total, v);
             }
         }
         __syncthreads();
@@ -144,8 +143,8 @@ __global__ void __launch_bounds__(32) k_combine(const xyzz_t *__restrict__ parts
     __shared__ xyzz_t sh[16];
     const int lane = threadIdx.x;
     xyzz_t v;
-    Ec<C>::set_inf(v);
-    for (int k = lane; k < count; k += 32) { xyzz_t t; load_xyzz(t, parts + k); Ec<C>::add_ni(v, t); }
+    Grp<C>::set_inf(v);
+    for (int k = lane; k < count; k += 32) { xyzz_t t; load_xyzz(t, parts + k); Grp<C>::add_ni(v, t); }
     warp_sum<C>(v, sh);
     if (lane == 0) export_jacobian<C>(v, out_jac);
 }
@@ -174,16 +173,21 @@ __global__ void __launch_bounds__(128) k_convert_points(const uint8_t *__restric
 }
 // table 0 back as arkworks (x, y) records of 96 bytes (tests)
 template <class C>
-__global__ void __launch_bounds__(128) k_export_points(const affine_t *__restrict__ table0, uint32_t n, uint32_t *__restrict__ dst) {
+__global__ void __launch_bounds__(128) k_export_points(const typename Grp<C>::entry_t *__restrict__ entries, uint32_t n, uint32_t *__restrict__ dst) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    affine_t a;
-    load_affine(a, table0 + i);
+    fp x, y;
+    Grp<C>::entry_to_sw(x, y, entries[i]);
     fp_abi ox, oy;
-    Ec<C>::to_abi_ni(ox, a.x);
-    Ec<C>::to_abi_ni(oy, a.y);
+    Ec<C>::to_abi_ni(ox, x);
+    Ec<C>::to_abi_ni(oy, y);
 #pragma unroll
     for (int k = 0; k < 12; k++) { dst[(size_t)i * 24 + k] = ox.w[k]; dst[(size_t)i * 24 + 12 + k] = oy.w[k]; }
+}
+// short-Weierstrass affine chunk -> table entries in the curve's bucket coordinates (grp.cuh)
+template <class C>
+__global__ void __launch_bounds__(128) k_make_entries(const affine_t *__restrict__ src, uint32_t n, typename Grp<C>::entry_t *__restrict__ dst) {
+    Grp<C>::make_entries(src, n, dst, blockIdx.x * blockDim.x + threadIdx.x);
 }
 // tmp[i] = 2^k * src[i]  (XYZZ, not normalised)
 template <class C>
@@ -323,6 +327,55 @@ __global__ void k_test_ec(int op, xyzz_abi_t *acc, const void *other, uint32_t n
         else if (op == 3) E::dbl_affine_ni(q, a.x, a.y);
     }
     E::to_abi_ni(acc[i].x, q.x); E::to_abi_ni(acc[i].y, q.y); E::to_abi_ni(acc[i].zz, q.zz); E::to_abi_ni(acc[i].zzz, q.zzz);
+}
+
+// group-law test: a, b short-Weierstrass affine (arkworks 96-byte records) -> entry / bucket coordinates -> op ->
+// back to an arkworks G1Affine record (104 bytes: x, y, infinity flag).  op 0: a + reps x b through the mixed add on
+// a table entry; 1: the same through the full add; 2: 2^reps a; 3: a - b (negated entry).
+template <class C>
+__global__ void k_test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps) {
+    typedef Grp<C> G;
+    __shared__ affine_t sw[2][64];
+    __shared__ typename G::entry_t ent[2][64];
+    __shared__ uint4 stage[G::ENTRY_VEC][64];
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t srci = i < n ? i : 0;         // pad the conversion batch with a valid point
+    Ec<C>::from_abi_ni(sw[0][lane].x, a[srci].x); Ec<C>::from_abi_ni(sw[0][lane].y, a[srci].y);
+    Ec<C>::from_abi_ni(sw[1][lane].x, b[srci].x); Ec<C>::from_abi_ni(sw[1][lane].y, b[srci].y);
+    __syncthreads();
+    // GRP_BATCH consecutive points per converting thread
+    if (lane < 64 / GRP_BATCH) { G::make_entries(sw[0], 64, ent[0], lane); G::make_entries(sw[1], 64, ent[1], lane); }
+    __syncthreads();
+    if (i >= n) return;
+    xyzz_t acc, other;
+    G::set_inf(acc);
+    G::set_inf(other);
+    auto put = [&](const typename G::entry_t &e) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(&e);
+#pragma unroll
+        for (int k = 0; k < G::ENTRY_VEC; k++) stage[k][lane] = s[k];
+    };
+    put(ent[0][lane]);
+    G::madd_staged(acc, &stage[0][lane], 64, false);             // acc = a
+    put(ent[1][lane]);
+    G::madd_staged(other, &stage[0][lane], 64, false);           // other = b
+    for (int k = 0; k < reps; k++) {
+        if (op == 0) G::madd_staged(acc, &stage[0][lane], 64, false);
+        else if (op == 1) G::add_ni(acc, other);
+        else if (op == 2) G::dbl_ni(acc);
+        else G::madd_staged(acc, &stage[0][lane], 64, true);
+    }
+    fp x, y;
+    const bool finite = G::to_sw_affine(x, y, acc);
+    fp_abi ox, oy;
+    if (!finite) { Fp<C>::set_zero(x); Fp<C>::set_one(y); }
+    Ec<C>::to_abi_ni(ox, x); Ec<C>::to_abi_ni(oy, y);
+    uint32_t *o = out104 + (size_t)i * 26;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { o[k] = ox.w[k]; o[12 + k] = oy.w[k]; }
+    o[24] = finite ? 0u : 1u;
+    o[25] = 0;
 }
 
 }  // namespace b200msm

@@ -154,13 +154,14 @@ __global__ void __launch_bounds__(PIECE_TPB) k_piece_order(const uint32_t *__res
 
 // ---------------------------------------------------------------------------------------------
 // a11 (curve-independent part)
-// replicate the first `have` entries of a table up to n (vector doubling, as the reference generator does)
-__global__ void __launch_bounds__(256) k_replicate(affine_t *table, uint32_t have, uint32_t n) {
+// replicate the first `have` entries of a table (vec 16-byte chunks each) up to n (vector doubling, as the reference
+// generator does)
+__global__ void __launch_bounds__(256) k_replicate(uint4 *table, uint32_t have, uint32_t n, uint32_t vec) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one uint4 per thread
-    size_t total = (size_t)(n - have) * AFF_VEC;
+    size_t total = (size_t)(n - have) * vec;
     if (idx >= total) return;
-    size_t e = have + idx / AFF_VEC, k = idx % AFF_VEC;
-    reinterpret_cast<uint4 *>(table + e)[k] = reinterpret_cast<const uint4 *>(table + (e % have))[k];
+    size_t e = have + idx / vec, k = idx % vec;
+    table[e * vec + k] = table[(e % have) * vec + k];
 }
 
 }  // namespace b200msm

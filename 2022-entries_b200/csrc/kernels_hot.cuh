@@ -95,28 +95,31 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
 }
 
 // ---------------------------------------------------------------------------------------------
-// a6: bucket accumulation.  One thread sums one piece: acc (XYZZ, registers) += table[ref] for each reference in
-// the piece.  The next point's 96 bytes are fetched with six 16-byte cp.async into the thread's own shared-memory
-// slots ([stage][16-byte chunk][thread]: conflict-free) while the current mixed add (~3000 integer instructions)
-// runs, so the random gather latency is hidden by one stage of prefetch.  Results go to res[piece].
+// a6: bucket accumulation.  One thread sums one piece: acc (registers) += table[ref] for each reference in the piece,
+// in the curve's bucket coordinates (grp.cuh: twisted-Edwards 7 M unified add on BLS12-377, XYZZ on BLS12-381).
+// The next entry (144 / 112 bytes) is fetched with 16-byte cp.async into the thread's own shared-memory slots
+// ([stage][16-byte chunk][thread]: conflict-free) while the current mixed add (~5000 integer instructions) runs, so the
+// random gather latency is hidden by one stage of prefetch.  Results go to res[piece].
 template <class C>
-__global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const affine_t *__restrict__ tables, const uint32_t *__restrict__ refs,
-                                                        const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
-                                                        const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
-                                                        xyzz_t *__restrict__ res) {
-    __shared__ uint4 stage[2][AFF_VEC][ACC_TPB];
+__global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+                                                           const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
+                                                           const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
+                                                           xyzz_t *__restrict__ res) {
+    typedef Grp<C> G;
+    constexpr int EV = G::ENTRY_VEC;
+    __shared__ uint4 stage[2][EV][ACC_TPB];
     uint32_t j = blockIdx.x * ACC_TPB + threadIdx.x;
     if (j >= *npieces_ptr) return;
     const uint32_t piece = order[j];
     const uint32_t start = piece_start[piece], len = piece_len[piece];
     xyzz_t acc;
-    Ec<C>::set_inf(acc);
+    G::set_inf(acc);
     uint32_t ref = 0, ref_next = 0;
     if (len) {
         ref = __ldg(refs + start);
         const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref & 0x7fffffffu));
 #pragma unroll
-        for (int k = 0; k < AFF_VEC; k++) cp_async16(&stage[0][k][threadIdx.x], src + k);
+        for (int k = 0; k < EV; k++) cp_async16(&stage[0][k][threadIdx.x], src + k);
     }
     cp_async_commit();
     for (uint32_t i = 0; i < len; i++) {
@@ -124,16 +127,11 @@ __global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const affine_t *__res
             ref_next = __ldg(refs + start + i + 1);
             const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref_next & 0x7fffffffu));
 #pragma unroll
-            for (int k = 0; k < AFF_VEC; k++) cp_async16(&stage[(i + 1) & 1][k][threadIdx.x], src + k);
+            for (int k = 0; k < EV; k++) cp_async16(&stage[(i + 1) & 1][k][threadIdx.x], src + k);
         }
         cp_async_commit();
         cp_async_wait<1>();
-        affine_t pt;
-        uint4 *t = reinterpret_cast<uint4 *>(&pt);
-#pragma unroll
-        for (int k = 0; k < AFF_VEC; k++) t[k] = stage[i & 1][k][threadIdx.x];
-        if (ref >> 31) Fp<C>::template neg<2>(pt.y, pt.y);
-        Ec<C>::madd(acc, pt.x, pt.y);
+        G::madd_staged(acc, &stage[i & 1][0][threadIdx.x], ACC_TPB, (ref >> 31) != 0);
         ref = ref_next;
     }
     store_xyzz(res + piece, acc);

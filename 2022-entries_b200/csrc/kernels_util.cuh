@@ -1,7 +1,7 @@
 // kernels_util.cuh -- device helpers shared by the kernel headers (async copies, 16-byte vector moves, RNG).
 #pragma once
 #include <cuda_runtime.h>
-#include "ec.cuh"
+#include "grp.cuh"
 
 namespace b200msm {
 

@@ -2,7 +2,7 @@
 // their own translation unit (inst_*.cu) so the library builds in parallel; msm.cu only sees these declarations.
 #pragma once
 #include <cuda_runtime.h>
-#include "ec.cuh"
+#include "grp.cuh"
 
 namespace b200msm {
 
@@ -15,7 +15,7 @@ struct fin_args_t { fin_term_t term[FIN_MAX_TERMS]; int nterms; int F; int c; };
 template <class C> struct LaunchHot {
     static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
                        int c, int W, int F, uint32_t *counters, uint32_t *refs);
-    static void accumulate(cudaStream_t st, uint32_t max_pieces, const affine_t *tables, const uint32_t *refs, const uint32_t *order,
+    static void accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,
                            const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res);
 };
 template <class C> struct LaunchCold {
@@ -29,7 +29,10 @@ template <class C> struct LaunchCold {
     static void gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp);
     static void gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out);
     static void convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask);
-    static void export_points(cudaStream_t st, const affine_t *table0, uint32_t n, uint32_t *dst);
+    static void export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst);
+    static void make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries);
+    static size_t entry_bytes();
+    static void test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps);
     static void generator(fp &gx, fp &gy);      // host: the curve generator in the device representation
     static void test_fp(int op, const fp_abi *a, const fp_abi *b, fp_abi *r, uint32_t n);
     static void test_ec(int op, xyzz_abi_t *acc, const void *other, uint32_t n, int reps);

@@ -11,9 +11,9 @@ void LaunchHot<C>::digits(int pass, cudaStream_t st, const uint32_t *scalars, co
     else k_digits<C, 1><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, table_stride, c, W, F, counters, refs);
 }
 template <class C>
-void LaunchHot<C>::accumulate(cudaStream_t st, uint32_t max_pieces, const affine_t *tables, const uint32_t *refs, const uint32_t *order,
+void LaunchHot<C>::accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,
                               const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res) {
-    k_accumulate<C><<<cdiv(max_pieces, ACC_TPB), ACC_TPB, 0, st>>>(tables, refs, order, piece_start, piece_len, npieces_ptr, res);
+    k_accumulate<C><<<cdiv(max_pieces, ACC_TPB), ACC_TPB, 0, st>>>((const typename Grp<C>::entry_t *)tables, refs, order, piece_start, piece_len, npieces_ptr, res);
 }
 
 }  // namespace b200msm

@@ -46,7 +46,8 @@ struct b200msm_ctx {
     int launches = 0;
 
     // device memory
-    affine_t *tables = nullptr;
+    uint8_t *tables = nullptr;          // T tables of n entries in the curve's bucket coordinates (grp.cuh)
+    size_t entry_bytes = 0;
     uint32_t *infmask = nullptr;
     uint32_t *counts = nullptr, *bucket_off = nullptr, *cursor = nullptr, *piece_off = nullptr;
     uint32_t *piece_start = nullptr, *piece_len = nullptr, *order = nullptr, *len_hist = nullptr, *len_cursor = nullptr;
@@ -88,7 +89,7 @@ static int scalar_bits(int curve) { return curve == 0 ? Bls12_377::SCALAR_BITS :
 // T limited by device memory (96 n bytes per table) and by the 31-bit point reference (T*n < 2^31).
 static void choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
     const int sb = scalar_bits(ctx->curve);
-    uint64_t tmax_mem = (uint64_t)((double)free_bytes * 0.55 / (96.0 * (double)n));
+    uint64_t tmax_mem = (uint64_t)((double)free_bytes * 0.72 / ((double)ctx->entry_bytes * (double)n));
     uint64_t tmax_ref = ((1ull << 31) - 1) / n;
     uint64_t tmax = tmax_mem < tmax_ref ? tmax_mem : tmax_ref;
     if (tmax < 1) tmax = 1;
@@ -131,7 +132,7 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     ctx->lmax = lmax;
     ctx->max_pieces = ctx->nbuckets + (uint32_t)(ctx->max_refs / lmax) + 1;
     const uint32_t nb = ctx->nbuckets;
-    CK(dmalloc(&ctx->tables, (size_t)ctx->T * n));
+    CK(dmalloc(&ctx->tables, (size_t)ctx->T * n * ctx->entry_bytes));
     CK(dmalloc(&ctx->infmask, (size_t)cdiv(n, 32) + 1));
     CK(dmalloc(&ctx->counts, (size_t)nb + 1));
     CK(dmalloc(&ctx->bucket_off, (size_t)nb + 1));
@@ -197,48 +198,74 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <class C> static int build_tables_t(b200msm_ctx *ctx) {
-    // tables[j] = 2^(c*F) * tables[j-1], normalised to affine; chunked so the XYZZ scratch stays small
-    const uint32_t n = (uint32_t)ctx->n;
-    const uint32_t chunk = 1u << 22;
-    xyzz_t *tmp = nullptr;
-    uint32_t tn = n < chunk ? n : chunk;
-    CK(dmalloc(&tmp, tn));
-    for (int j = 1; j < ctx->T; j++) {
-        for (uint32_t first = 0; first < n; first += chunk) {
-            uint32_t cnt = n - first < chunk ? n - first : chunk;
-            const affine_t *src = ctx->tables + (size_t)(j - 1) * n + first;
-            affine_t *dst = ctx->tables + (size_t)j * n + first;
-            LaunchCold<C>::double_n(ctx->stream, src, cnt, ctx->c * ctx->F, tmp);
-            LaunchCold<C>::batch_normalize(ctx->stream, tmp, cnt, dst);
-        }
-    }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
+// a11: base tables.  Per chunk of <= 2^22 points: table 0 entry = the point itself, table j = 2^(c*F) * table j-1,
+// doubled in XYZZ, normalised to short-Weierstrass affine (one inversion per 16 points), then converted to the curve's
+// table-entry form.  Only two affine chunk buffers and one XYZZ chunk buffer of scratch are alive.
+struct table_scratch_t { affine_t *sw[2] = {nullptr, nullptr}; xyzz_t *tmp = nullptr; uint32_t cap = 0; };
+static int scratch_alloc(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t cap) {
+    sc.cap = cap;
+    CK(dmalloc(&sc.sw[0], cap)); CK(dmalloc(&sc.sw[1], cap)); CK(dmalloc(&sc.tmp, cap));
     return 0;
 }
-static int build_tables(b200msm_ctx *ctx) { return ctx->curve == 0 ? build_tables_t<Bls12_377>(ctx) : build_tables_t<Bls12_381>(ctx); }
+static void scratch_free(table_scratch_t &sc) { cudaFree(sc.sw[0]); cudaFree(sc.sw[1]); cudaFree(sc.tmp); }
+// sc.sw[0] holds cnt affine points starting at index `first`: emit their entries into every table
+template <class C> static void emit_tables(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t first, uint32_t cnt) {
+    const size_t eb = ctx->entry_bytes;
+    int cur = 0;
+    for (int j = 0; j < ctx->T; j++) {
+        if (j > 0) {
+            LaunchCold<C>::double_n(ctx->stream, sc.sw[cur], cnt, ctx->c * ctx->F, sc.tmp);
+            LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[cur ^ 1]);
+            cur ^= 1;
+        }
+        LaunchCold<C>::make_entries(ctx->stream, sc.sw[cur], cnt, ctx->tables + ((size_t)j * ctx->n + first) * eb);
+    }
+    if (cur != 0) { affine_t *t = sc.sw[0]; sc.sw[0] = sc.sw[1]; sc.sw[1] = t; }
+}
 
 template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int mode, uint64_t distinct, const fp &gx, const fp &gy) {
     const uint32_t n = (uint32_t)ctx->n;
     uint32_t gen_n = mode == 0 ? (uint32_t)(distinct < n ? distinct : n) : n;
     const uint32_t chunk = 1u << 22;
-    xyzz_t *tmp = nullptr;
-    CK(dmalloc(&tmp, gen_n < chunk ? gen_n : chunk));
+    table_scratch_t sc;
+    int rc = scratch_alloc(ctx, sc, gen_n < chunk ? gen_n : chunk); if (rc) return rc;
     for (uint32_t first = 0; first < gen_n; first += chunk) {
         uint32_t cnt = gen_n - first < chunk ? gen_n - first : chunk;
-        LaunchCold<C>::gen_points(ctx->stream, first, cnt, seed, mode, (uint32_t)(distinct ? distinct : 1), gx, gy, tmp);
-        LaunchCold<C>::batch_normalize(ctx->stream, tmp, cnt, ctx->tables + first);
+        LaunchCold<C>::gen_points(ctx->stream, first, cnt, seed, mode, (uint32_t)(distinct ? distinct : 1), gx, gy, sc.tmp);
+        LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[0]);
+        emit_tables<C>(ctx, sc, first, cnt);
     }
-    if (gen_n < n) {
-        uint64_t work = (uint64_t)(n - gen_n) * AFF_VEC;
-        k_replicate<<<cdiv(work, 256), 256, 0, ctx->stream>>>(ctx->tables, gen_n, n);
+    if (gen_n < n) {        // the replicas of a point have the same entry in every table
+        const uint32_t vec = (uint32_t)(ctx->entry_bytes / 16);
+        for (int j = 0; j < ctx->T; j++) {
+            uint64_t work = (uint64_t)(n - gen_n) * vec;
+            k_replicate<<<cdiv(work, 256), 256, 0, ctx->stream>>>((uint4 *)(ctx->tables + (size_t)j * n * ctx->entry_bytes), gen_n, n, vec);
+        }
     }
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
+    scratch_free(sc);
+    return 0;
+}
+
+template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride) {
+    const uint64_t chunk = 1ull << 22;
+    table_scratch_t sc;
+    int rc = scratch_alloc(ctx, sc, (uint32_t)(n < chunk ? n : chunk)); if (rc) return rc;
+    uint8_t *raw = nullptr;
+    CK(cudaMalloc((void **)&raw, (size_t)((n < chunk ? n : chunk) * stride)));
+    CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
+    for (uint64_t first = 0; first < n; first += chunk) {
+        uint64_t cnt = n - first < chunk ? n - first : chunk;
+        CK(cudaMemcpyAsync(raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), cudaMemcpyHostToDevice, ctx->stream));
+        LaunchCold<C>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, sc.sw[0], ctx->infmask + first / 32);
+        emit_tables<C>(ctx, sc, (uint32_t)first, (uint32_t)cnt);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(raw);
+    scratch_free(sc);
     return 0;
 }
 
@@ -357,6 +384,7 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     if (device < 0 || device >= ndev) { g_create_error = "b200msm_create: bad device index"; return -1; }
     b200msm_ctx *ctx = new b200msm_ctx();
     ctx->curve = curve; ctx->device = device; ctx->req_c = window_bits; ctx->req_tables = tables;
+    ctx->entry_bytes = curve == 0 ? LaunchCold<Bls12_377>::entry_bytes() : LaunchCold<Bls12_381>::entry_bytes();
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -405,20 +433,7 @@ int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uin
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!affine_host || n == 0 || n >= (1ull << 31) || stride < 96 || (stride & 7)) return ctx->fail(-1, "b200msm_set_bases: bad argument");
     rc = alloc_plan(ctx, n); if (rc) return rc;
-    // stage the arkworks records through device memory in chunks
-    const uint64_t chunk = 1ull << 22;
-    uint8_t *raw = nullptr;
-    CK(cudaMalloc((void **)&raw, (size_t)((n < chunk ? n : chunk) * stride)));
-    CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
-    for (uint64_t first = 0; first < n; first += chunk) {
-        uint64_t cnt = n - first < chunk ? n - first : chunk;
-        CK(cudaMemcpyAsync(raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), cudaMemcpyHostToDevice, ctx->stream));
-        if (ctx->curve == 0) LaunchCold<Bls12_377>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, ctx->tables + first, ctx->infmask + first / 32);
-        else LaunchCold<Bls12_381>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, ctx->tables + first, ctx->infmask + first / 32);
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    cudaFree(raw);
-    return build_tables(ctx);
+    return ctx->curve == 0 ? set_bases_t<Bls12_377>(ctx, affine_host, n, stride) : set_bases_t<Bls12_381>(ctx, affine_host, n, stride);
 }
 
 int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int mode, uint64_t distinct) {
@@ -428,9 +443,7 @@ int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int
     rc = alloc_plan(ctx, n); if (rc) return rc;
     fp gx, gy;
     generator(ctx->curve, gx, gy);
-    rc = ctx->curve == 0 ? gen_bases_t<Bls12_377>(ctx, seed, mode, distinct, gx, gy) : gen_bases_t<Bls12_381>(ctx, seed, mode, distinct, gx, gy);
-    if (rc) return rc;
-    return build_tables(ctx);
+    return ctx->curve == 0 ? gen_bases_t<Bls12_377>(ctx, seed, mode, distinct, gx, gy) : gen_bases_t<Bls12_381>(ctx, seed, mode, distinct, gx, gy);
 }
 
 int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uint64_t n) {
@@ -439,8 +452,8 @@ int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uin
     CK(cudaStreamSynchronize(ctx->stream));
     uint32_t *tmp = nullptr;
     CK(cudaMalloc((void **)&tmp, (size_t)n * 96));
-    if (ctx->curve == 0) LaunchCold<Bls12_377>::export_points(ctx->stream, ctx->tables + first, (uint32_t)n, tmp);
-    else LaunchCold<Bls12_381>::export_points(ctx->stream, ctx->tables + first, (uint32_t)n, tmp);
+    if (ctx->curve == 0) LaunchCold<Bls12_377>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp);
+    else LaunchCold<Bls12_381>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(affine96_host, tmp, (size_t)n * 96, cudaMemcpyDeviceToHost));
     cudaFree(tmp);
@@ -580,6 +593,19 @@ int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t
     TCK(cudaGetLastError());
     TCK(cudaMemcpy(acc, dacc, (size_t)n * 192, cudaMemcpyDeviceToHost));
     cudaFree(dacc); if (doth) cudaFree(doth);
+    return 0;
+}
+
+int b200msm_test_grp_op(int curve, int op, const void *a96, const void *b96, void *out104, uint64_t n, int reps) {
+    if (!a96 || !b96 || !out104 || n == 0 || (curve != 0 && curve != 1) || op < 0 || op > 3 || reps < 0) return -1;
+    affine_abi_t *da, *db; uint32_t *dout;
+    TCK(cudaMalloc((void **)&da, (size_t)n * 96)); TCK(cudaMalloc((void **)&db, (size_t)n * 96)); TCK(cudaMalloc((void **)&dout, (size_t)n * 104));
+    TCK(cudaMemcpy(da, a96, (size_t)n * 96, cudaMemcpyHostToDevice)); TCK(cudaMemcpy(db, b96, (size_t)n * 96, cudaMemcpyHostToDevice));
+    if (curve == 0) LaunchCold<Bls12_377>::test_grp(op, da, db, dout, (uint32_t)n, reps);
+    else LaunchCold<Bls12_381>::test_grp(op, da, db, dout, (uint32_t)n, reps);
+    TCK(cudaGetLastError());
+    TCK(cudaMemcpy(out104, dout, (size_t)n * 104, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout);
     return 0;
 }
 

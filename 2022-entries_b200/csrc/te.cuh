@@ -1,0 +1,184 @@
+// te.cuh -- bucket arithmetic in the twisted-Edwards model of the curve (BLS12-377 G1 has one; BLS12-381 does not).
+//
+//   E_te:  -x^2 + y^2 = 1 + d x^2 y^2,  extended coordinates (X : Y : Z : T), x = X/Z, y = Y/Z, T = XY/Z.
+//
+// Why: the accumulate kernel is bound by the integer-multiply pipe (fmaheavy 88 % busy, profiles/
+// r01_ncu_accumulate_v3_calls.txt), so the only way down is fewer multiplies per point.  With the base tables stored as
+// (y - x, y + x, 2 d x y) the unified mixed addition add-2008-hwcd-3 (a = -1) costs 7 multiplies against 8 M + 2 S for
+// XYZZ, and it is the SAME formula for P + Q, P + P, P + (-P) and P + 0: no infinity / doubling branches in the hot
+// loop.  d is a square here, so the law is not complete on the whole curve, but its exceptional pairs differ by a
+// point of even order; bases in G1 (prime order r) never meet one -- the same contract the reference's entries have
+// (matter-labs asserts !infinity and G1 membership is arkworks' deserialisation check).
+// The reference's Trapdoor-Tech entry uses the same model (P1A/Trapdoor-Tech/sppark/ec/exte_t.hpp:74-200,
+// msm_opt.md); the map below is derived from the curve equation (SW -> Montgomery -> TE, then x scaled so a = -1),
+// with arkworks' parameter values (P1B/nickray/driver/bls12-377/src/curves/g1.rs:52-113) as the cross-check.
+//
+//   SW (x, y), y^2 = x^3 + 1   ->   x' = f (x + 1) / y,   y' = (s (x + 1) - 1) / (s (x + 1) + 1)         s = 1/sqrt 3
+//   TE (X : Y : Z)             ->   x = sqrt3 (Z + Y) / (Z - Y) - 1,   y = (f / s) Z (Z + Y) / (X (Z - Y))
+//
+// Storage: a bucket is 4 field elements like XYZZ (struct xyzz_t reused: x = X, y = Y, zz = Z, zzz = T); a table entry
+// is the three precomputed values, canonical, bit-packed 12 x 32 each = 144 bytes (9 x 16: cp.async friendly).
+// Value bounds (units of p): every stored coordinate is a multiply output (< 2); the largest product below is 7 x 6.
+#pragma once
+#include "ec.cuh"
+
+namespace b200msm {
+
+struct te_entry_t { uint32_t w[36]; };       // (y - x, y + x, 2 d x y), each 12 x 32-bit packed canonical Montgomery
+struct te_pre_t { fp ymx, ypx, kt; };        // the same in registers
+
+template <class C> struct Te {
+    typedef Fp<C> F;
+    typedef Ec<C> E;
+
+    FP_HD static void load_const(fp &r, int which) {
+#pragma unroll
+        for (int i = 0; i < FP_LIMBS; i++)
+            r.l[i] = which == 0 ? C::te_k(i) : which == 1 ? C::te_f(i) : which == 2 ? C::te_s(i) : which == 3 ? C::te_s3(i) : C::te_cy(i);
+    }
+    FP_HD static void set_inf(xyzz_t &a) { F::set_zero(a.x); F::set_one(a.y); F::set_one(a.zz); F::set_zero(a.zzz); }
+    // the neutral element is the only point of G1 with X = 0
+    FP_HD static bool is_inf(const xyzz_t &a) { return F::is_zero(a.x); }
+
+    FP_HD static void unpack(te_pre_t &q, const te_entry_t &e) {
+        fp_abi t;
+#pragma unroll
+        for (int i = 0; i < 12; i++) t.w[i] = e.w[i];
+        F::repack_from_abi(q.ymx, t);
+#pragma unroll
+        for (int i = 0; i < 12; i++) t.w[i] = e.w[12 + i];
+        F::repack_from_abi(q.ypx, t);
+#pragma unroll
+        for (int i = 0; i < 12; i++) t.w[i] = e.w[24 + i];
+        F::repack_from_abi(q.kt, t);
+    }
+    // canonicalise (< p) and pack
+    FP_HD static void pack(te_entry_t &e, te_pre_t q) {
+        F::reduce(q.ymx); F::reduce(q.ypx); F::reduce(q.kt);
+        fp_abi t;
+        F::repack_to_abi(t, q.ymx);
+#pragma unroll
+        for (int i = 0; i < 12; i++) e.w[i] = t.w[i];
+        F::repack_to_abi(t, q.ypx);
+#pragma unroll
+        for (int i = 0; i < 12; i++) e.w[12 + i] = t.w[i];
+        F::repack_to_abi(t, q.kt);
+#pragma unroll
+        for (int i = 0; i < 12; i++) e.w[24 + i] = t.w[i];
+    }
+    // -(x, y) = (-x, y): swap the first two values, negate the third
+    FP_HD static void negate(te_pre_t &q) {
+        fp t = q.ymx; q.ymx = q.ypx; q.ypx = t;
+        F::template neg<2>(q.kt, q.kt);
+    }
+
+    // acc += q   (add-2008-hwcd-3 with Z2 = 1 and k T2 precomputed: 7 M)
+    FP_HD static void madd(xyzz_t &acc, const te_pre_t &q) {
+        fp a, b, c, d, e, f, g, h;
+        F::template sub<3>(a, acc.y, acc.x);      // Y1 - X1                    5
+        E::M(a, a, q.ymx);                        // A                          2
+        F::add(b, acc.y, acc.x);                  // Y1 + X1                    4
+        E::M(b, b, q.ypx);                        // B                          2
+        E::M(c, acc.zzz, q.kt);                   // C = T1 * 2 d t2            2
+        F::add(d, acc.zz, acc.zz);                // D = 2 Z1                   4
+        F::template sub<3>(e, b, a);              // E = B - A                  5
+        F::template sub<3>(f, d, c);              // F = D - C                  7
+        F::add(g, d, c);                          // G = D + C                  6
+        F::add(h, b, a);                          // H = B + A                  4
+        E::M(acc.x, e, f);                        // X3 = E F
+        E::M(acc.y, g, h);                        // Y3 = G H
+        E::M(acc.zzz, e, h);                      // T3 = E H
+        E::M(acc.zz, f, g);                       // Z3 = F G
+    }
+    // a += b, both extended (add-2008-hwcd-3: 9 M); also doubles (b may equal a)
+    FP_HD static void add(xyzz_t &a, const xyzz_t &b) {
+        fp A, B, Cc, D, e, f, g, h, t, k;
+        F::template sub<3>(A, a.y, a.x);
+        F::template sub<3>(t, b.y, b.x);
+        E::M(A, A, t);                            // A = (Y1 - X1)(Y2 - X2)     5 x 5
+        F::add(B, a.y, a.x);
+        F::add(t, b.y, b.x);
+        E::M(B, B, t);                            // B = (Y1 + X1)(Y2 + X2)     4 x 4
+        load_const(k, 0);
+        E::M(Cc, a.zzz, b.zzz);
+        E::M(Cc, Cc, k);                          // C = 2 d T1 T2
+        E::M(D, a.zz, b.zz);
+        F::add(D, D, D);                          // D = 2 Z1 Z2                4
+        F::template sub<3>(e, B, A);
+        F::template sub<3>(f, D, Cc);
+        F::add(g, D, Cc);
+        F::add(h, B, A);
+        E::M(a.x, e, f);
+        E::M(a.y, g, h);
+        E::M(a.zzz, e, h);
+        E::M(a.zz, f, g);
+    }
+    FP_HD static void dbl(xyzz_t &a) {
+        xyzz_t b = a;
+        add(a, b);
+    }
+
+    // short-Weierstrass affine (x, y) -> (numerators, denominator) of the map; the caller inverts den (batched):
+    //   x' = nu * (dv / den),  y' = nv * (y / den),  den = y * dv
+    FP_HD static void map_prepare(fp &nu, fp &nv, fp &dv, fp &den, const fp &x, const fp &y) {
+        fp one, t1, xm, cf, cs;
+        F::set_one(one);
+        load_const(cf, 1);
+        load_const(cs, 2);
+        F::add(t1, x, one);                       // x + 1                      2
+        E::M(nu, t1, cf);                         // f (x + 1)
+        E::M(xm, t1, cs);                         // s (x + 1)
+        F::add(dv, xm, one);                      // s (x + 1) + 1              3
+        F::template sub<2>(nv, xm, one);          // s (x + 1) - 1              4
+        E::M(den, y, dv);
+    }
+    // inv = 1 / den  ->  table entry
+    FP_HD static void map_finish(te_entry_t &out, const fp &nu, const fp &nv, const fp &dv, const fp &y, const fp &inv) {
+        fp iy, idv, u, v, k;
+        E::M(iy, inv, dv);                        // 1 / y
+        E::M(idv, inv, y);                        // 1 / dv
+        E::M(u, nu, iy);
+        E::M(v, nv, idv);
+        te_pre_t q;
+        F::template sub<3>(q.ymx, v, u);
+        F::add(q.ypx, v, u);
+        load_const(k, 0);
+        E::M(q.kt, u, v);
+        E::M(q.kt, q.kt, k);
+        pack(out, q);
+    }
+    // extended point -> short-Weierstrass affine (canonical); false for the neutral element.  One inversion.
+    FP_HD static bool to_sw_affine(fp &x, fp &y, const xyzz_t &a) {
+        if (is_inf(a)) return false;
+        fp zmy, zpy, den, inv, t, one, c3, cy;
+        F::template sub<3>(zmy, a.zz, a.y);       // Z - Y
+        F::add(zpy, a.zz, a.y);                   // Z + Y
+        E::M(den, a.x, zmy);
+        F::inv(inv, den);
+        E::M(t, zpy, inv);                        // (Z + Y) / (X (Z - Y))
+        load_const(c3, 3);
+        load_const(cy, 4);
+        F::set_one(one);
+        E::M(x, t, a.x);                          // (Z + Y) / (Z - Y)
+        E::M(x, x, c3);
+        F::template sub<2>(x, x, one);            // sqrt3 xm - 1
+        E::M(y, t, a.zz);
+        E::M(y, y, cy);
+        F::reduce(x);
+        F::reduce(y);
+        return true;
+    }
+    // table entry -> extended point (2x' : 2y' : 2 : .)  (tests: read the bases back)
+    FP_HD static void entry_to_point(xyzz_t &a, const te_entry_t &e) {
+        te_pre_t q;
+        unpack(q, e);
+        fp one;
+        F::set_one(one);
+        F::template sub<2>(a.x, q.ypx, q.ymx);
+        F::add(a.y, q.ypx, q.ymx);
+        F::add(a.zz, one, one);
+        F::set_zero(a.zzz);                       // T is not needed by to_sw_affine
+    }
+};
+
+}  // namespace b200msm

@@ -296,11 +296,12 @@ def main():
         alg_bytes = n_local * 128
         achieved = alg_bytes / (acc_ms / 1e3) / 1e9
         # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (10 modmul: 8 mul x 378 + 2 sqr x 301) vs the
-        # measured issue rate of plain IMAD.WIDE.U32 (profiles/r01_imad_microbench.txt: 63 / clk / SM)
+        # measured IMAD.WIDE.U32 rate: 32 lanes / clk / SM -- the fmaheavy pipe is 89 % busy when the multiplier
+        # microbenchmark sustains 378 IMAD.WIDE per 13.2 SM-clocks (profiles/r01_mul_bench.txt)
         madds = info["windows"] * n_local
         imad_per_madd = 8 * 378 + 2 * 301
         sm_mhz = clocks["sm_mhz"] or 1965
-        int_peak = 63.0 * 148 * sm_mhz * 1e6
+        int_peak = 32.0 * 148 * sm_mhz * 1e6
         int_ach = madds * imad_per_madd / (acc_ms / 1e3)
         line = {
             "metric": METRIC.format(lg=lg), "value": n / (ms_dev / 1e3), "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -316,7 +317,7 @@ def main():
                          "peak_source": peak_src, "ms_per_launch": acc_ms, "algorithmic_bytes": alg_bytes,
                          "note": "integer-pipe bound by construction; see int_pipe"},
             "int_pipe": {"imad_wide_per_launch": madds * imad_per_madd, "achieved_per_s": int_ach, "peak_per_s": int_peak, "frac": int_ach / int_peak,
-                         "peak_source": "63 IMAD.WIDE/clk/SM measured (profiles/r01_imad_microbench.txt) x 148 SMs x sampled SM clock"},
+                         "peak_source": "32 IMAD.WIDE lanes/clk/SM measured (profiles/r01_mul_bench.txt) x 148 SMs x sampled SM clock"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_msm * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -91,6 +91,11 @@ int b200msm_get_stage_ms_sum(b200msm_ctx *ctx, float stage_ms_sum[6], uint64_t *
  * ec op: 0 acc += affine(96 B), 1 acc += xyzz(192 B), 2 acc = 2 acc, 3 acc = 2 affine; acc is XYZZ (4 x 48 B). */
 int b200msm_test_fp_op(int curve, int op, const void *a, const void *b, void *r, uint64_t n);
 int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t n, int reps);
+/* Bucket coordinate system of the curve (twisted-Edwards extended on BLS12-377, XYZZ on BLS12-381), through the same
+ * table-entry conversion and mixed add the accumulate kernel uses.  a, b: n arkworks (x, y) records of 96 bytes, points
+ * of G1; out: n G1Affine records of 104 bytes.  op 0: a + reps*b (mixed add on a table entry), 1: the same through the
+ * full add, 2: 2^reps a, 3: a - reps*b. */
+int b200msm_test_grp_op(int curve, int op, const void *a96, const void *b96, void *out104, uint64_t n, int reps);
 
 /* ---- 1. Family A: sppark / organisers' harness ---------------------------------------------------------------- */
 typedef struct { int code; char *message; } RustError;   /* message is strdup'd; the Rust side frees it

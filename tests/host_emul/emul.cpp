@@ -3,7 +3,7 @@
 // without a GPU.  Built by tests/test_host_emul.py with g++; never part of the product library.
 #include <cstring>
 #include <cstddef>
-#include "../../2022-entries_b200/csrc/ec.cuh"
+#include "../../2022-entries_b200/csrc/te.cuh"
 using namespace b200msm;
 
 // All entry points take and return arkworks-ABI field elements (48 bytes, R = 2^384, canonical) and convert to the
@@ -73,7 +73,45 @@ template <class C> static void constants(uint32_t *out) {
     out[56] = C::INV; out[57] = C::P0INV;
     for (int k = 0; k < 16; k++) for (int i = 0; i < FP_LIMBS; i++) out[64 + k * 14 + i] = kp_dom<C>(k + 1, i);
 }
+// twisted-Edwards bucket arithmetic (te.cuh), BLS12-377: a, b short-Weierstrass affine (ABI) -> table entries -> op ->
+// back to short-Weierstrass affine.  op 0: a + reps*b (mixed), 1: the same by full adds, 2: 2^reps a, 3: a - reps*b.
+// out: x, y (ABI) and a flag word (1 = infinity)
+static void te_ops(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out, size_t n, int reps) {
+    typedef Bls12_377 C; typedef Fp<C> F; typedef Te<C> T;
+    for (size_t i = 0; i < n; i++) {
+        te_entry_t ent[2];
+        for (int k = 0; k < 2; k++) {
+            const affine_abi_t &s = k == 0 ? a[i] : b[i];
+            fp x, y, nu, nv, dv, den, inv;
+            F::from_abi(x, s.x); F::from_abi(y, s.y);
+            T::map_prepare(nu, nv, dv, den, x, y);
+            F::inv(inv, den);
+            T::map_finish(ent[k], nu, nv, dv, y, inv);
+        }
+        xyzz_t acc, other; te_pre_t q;
+        T::set_inf(acc); T::set_inf(other);
+        T::unpack(q, ent[0]); T::madd(acc, q);
+        T::unpack(q, ent[1]); T::madd(other, q);
+        for (int k = 0; k < reps; k++) {
+            if (op == 0) T::madd(acc, q);
+            else if (op == 1) T::add(acc, other);
+            else if (op == 2) T::dbl(acc);
+            else { te_pre_t nq = q; T::negate(nq); T::madd(acc, nq); }
+        }
+        fp x, y;
+        bool finite = T::to_sw_affine(x, y, acc);
+        if (!finite) { F::set_zero(x); F::set_one(y); }
+        fp_abi ox, oy; F::to_abi(ox, x); F::to_abi(oy, y);
+        for (int k = 0; k < 12; k++) { out[i * 26 + k] = ox.w[k]; out[i * 26 + 12 + k] = oy.w[k]; }
+        out[i * 26 + 24] = finite ? 0 : 1; out[i * 26 + 25] = 0;
+    }
+}
+template <class C> static void te_constants(uint32_t *out) {
+    for (int i = 0; i < FP_LIMBS; i++) { out[i] = C::te_k(i); out[14 + i] = C::te_f(i); out[28 + i] = C::te_s(i); out[42 + i] = C::te_s3(i); out[56 + i] = C::te_cy(i); }
+}
 extern "C" {
+int emul_te_op(int op, const void *a, const void *b, void *out, size_t n, int reps) { te_ops(op, (const affine_abi_t *)a, (const affine_abi_t *)b, (uint32_t *)out, n, reps); return 0; }
+int emul_te_constants(uint32_t *out) { te_constants<Bls12_377>(out); return 0; }
 int emul_fp_op(int curve, int op, const void *a, const void *b, void *r, size_t n) {
     if (curve == 0) fp_ops<Bls12_377>(op, (const fp_abi *)a, (const fp_abi *)b, (fp_abi *)r, n); else fp_ops<Bls12_381>(op, (const fp_abi *)a, (const fp_abi *)b, (fp_abi *)r, n);
     return 0;

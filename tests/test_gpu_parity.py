@@ -240,3 +240,33 @@ def test_point_sharding_partial_and_combine(M, oracle):
     for e in engs:
         e.close()
     assert np.array_equal(O.jac_to_affine(out.cpu().numpy()), O.jac_to_affine(O.ark_msm(pts, sc)))
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_bucket_coordinate_system_matches_oracle(M, oracle, curve):
+    """The group law the accumulate kernel uses (twisted-Edwards extended on BLS12-377, XYZZ on BLS12-381), through the
+    table-entry conversion, vs the oracle's Jacobian arithmetic -- incl. P + P, P - P and chains through the neutral."""
+    O = oracle
+    n = 200
+    A, B = O.gen_points(n, seed=15, curve=curve), O.gen_points(n, seed=19, curve=curve)
+    B[0] = A[0]
+    B[1] = O.aff_neg(A[1:2], curve)[0]
+    a96, b96 = np.ascontiguousarray(A[:, :96]), np.ascontiguousarray(B[:, :96])
+    one = np.frombuffer(O.constants(curve)["R"].to_bytes(48, "little"), np.uint8)
+    jacA = np.zeros((n, 144), np.uint8)
+    jacA[:, :96] = A[:, :96]
+    jacA[:, 96:] = one
+    for op, reps in ((0, 1), (0, 5), (1, 3), (2, 23), (3, 1), (3, 4), (0, 0)):
+        got = M.test_grp_op(curve, op, a96, b96, reps)
+        j = jacA.copy()
+        for _ in range(reps):
+            if op in (0, 1):
+                j = O.jac_add_mixed(j, B, curve)
+            elif op == 2:
+                j = O.jac_double(j, curve)
+            else:
+                j = O.jac_add_mixed(j, O.aff_neg(B, curve), curve)
+        want = O.jac_to_affine(j, curve)
+        assert np.array_equal(got[:, 96], want[:, 96]), (curve, op, reps)
+        fin = want[:, 96] == 0
+        assert np.array_equal(got[fin, :96], want[fin, :96]), (curve, op, reps)

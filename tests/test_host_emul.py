@@ -21,7 +21,7 @@ HERE = os.path.join(ROOT, "tests", "host_emul")
 def emul():
     so = os.path.join(HERE, "emul.so")
     src = os.path.join(HERE, "emul.cpp")
-    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "ec.cuh")]
+    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "ec.cuh", "te.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
     L = ctypes.CDLL(so)
@@ -30,6 +30,8 @@ def emul():
     L.emul_ec_op.argtypes = [i32, i32, vp, vp, sz, i32]
     L.emul_fp_mul_lazy.argtypes = [i32, vp, vp, vp, sz, i32, i32]
     L.emul_constants.argtypes = [i32, vp]
+    L.emul_te_op.argtypes = [i32, vp, vp, vp, sz, i32]
+    L.emul_te_constants.argtypes = [vp]
     return L
 
 
@@ -159,3 +161,47 @@ def test_curve_ops(emul, oracle, curve):
     a96 = np.ascontiguousarray(A[:, :96])
     emul.emul_ec_op(curve, 3, _p(da), _p(a96), n, 1)
     assert np.array_equal(O.xyzz_to_affine(da, curve), O.jac_to_affine(O.jac_double(_jac_from_aff(O, A, curve), curve), curve))
+
+
+def test_te_constants(emul):
+    """Twisted-Edwards parameters of BLS12-377 G1 re-derived from p: s = 1/sqrt 3, A = -3s, B = s, a1 = (A+2)/B,
+    d1 = (A-2)/B, f = sqrt(-a1), d = -d1/a1 (= arkworks' COEFF_D, P1B/nickray/driver/bls12-377/src/curves/g1.rs:93)."""
+    buf = np.zeros(70, np.uint32)
+    emul.emul_te_constants(_p(buf))
+    p = RB.CURVES[0]["p"]
+    R = (1 << 392) % p
+    val = lambda a: sum(int(x) << (28 * i) for i, x in enumerate(a)) * pow(R, -1, p) % p
+    k, f, s, s3, cy = (val(buf[14 * i: 14 * i + 14]) for i in range(5))
+    assert 3 * s * s % p == 1 and s * s3 % p == 1
+    A, B = (-3 * s) % p, s
+    a1, d1 = (A + 2) * pow(B, -1, p) % p, (A - 2) * pow(B, -1, p) % p
+    d = (-d1 * pow(a1, -1, p)) % p
+    assert d == 122268283598675559488486339158635529096981886914877139579534153582033676785385790730042363341236035746924960903179
+    assert k == 2 * d % p and f * f % p == (-a1) % p and cy == f * s3 % p
+
+
+def test_te_group_law(emul, oracle):
+    """Mixed add, full add, doubling and subtraction in twisted-Edwards coordinates == the oracle's Jacobian arithmetic,
+    including P + P, P - P and chains that pass through the neutral element."""
+    O = oracle
+    n = 48
+    A, B = O.gen_points(n, seed=5), O.gen_points(n, seed=9)
+    B[0] = A[0]                                   # P + P through the unified formula
+    B[1] = O.aff_neg(A[1:2])[0]                   # P - P -> neutral, then neutral + B ...
+    a96, b96 = np.ascontiguousarray(A[:, :96]), np.ascontiguousarray(B[:, :96])
+    out = np.zeros((n, 104), np.uint8)
+    jacA, jacB = _jac_from_aff(O, A, 0), _jac_from_aff(O, B, 0)
+    for op, reps in ((0, 1), (0, 5), (1, 3), (2, 23), (3, 1), (3, 4), (0, 0)):
+        emul.emul_te_op(op, _p(a96), _p(b96), _p(out), n, reps)
+        j = jacA.copy()
+        for _ in range(reps):
+            if op in (0, 1):
+                j = O.jac_add_mixed(j, B)
+            elif op == 2:
+                j = O.jac_double(j)
+            else:
+                j = O.jac_add_mixed(j, O.aff_neg(B))
+        want = O.jac_to_affine(j)
+        assert np.array_equal(out[:, 96], want[:, 96]), (op, reps)
+        fin = want[:, 96] == 0
+        assert np.array_equal(out[fin, :96], want[fin, :96]), (op, reps)
