@@ -14,8 +14,12 @@ template <class C> struct GrpXyzz {
     typedef Fp<C> F;
     typedef affine_t entry_t;
     static constexpr int ENTRY_VEC = sizeof(affine_t) / 16;       // 7
+    typedef xyzz_t acc_t;                                         // the accumulate kernel's register accumulator
     FP_HD static void set_inf(xyzz_t &a) { Ec<C>::set_inf(a); }
 #if defined(__CUDACC__)
+    __device__ __forceinline__ static void acc_init(acc_t &a) { Ec<C>::set_inf(a); }
+    __device__ __forceinline__ static void acc_madd_staged(acc_t &acc, const uint4 *st, int stride, bool negate) { madd_staged(acc, st, stride, negate); }
+    __device__ __forceinline__ static void acc_export(xyzz_t &out, const acc_t &a) { out = a; }
     // acc += entry, the entry staged as ENTRY_VEC 16-byte chunks `stride` uint4 apart
     __device__ __forceinline__ static void madd_staged(xyzz_t &acc, const uint4 *st, int stride, bool negate) {
         affine_t pt;
@@ -33,7 +37,7 @@ template <class C> struct GrpXyzz {
         return true;
     }
     // thread t converts src[t*GRP_BATCH ...] (short-Weierstrass affine, canonical) to entries: a copy here
-    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t) {
+    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t, bool /*ark*/) {
         for (uint32_t k = 0; k < GRP_BATCH; k++) {
             const uint32_t i = t * GRP_BATCH + k;
             if (i >= n) return;
@@ -43,7 +47,7 @@ template <class C> struct GrpXyzz {
             for (int v = 0; v < ENTRY_VEC; v++) d[v] = s[v];
         }
     }
-    __device__ static void entry_to_sw(fp &x, fp &y, const entry_t &e) { x = e.x; y = e.y; }
+    __device__ static void entry_to_sw(fp &x, fp &y, const entry_t &e, bool /*ark*/) { x = e.x; y = e.y; }
 #endif
 };
 
@@ -51,8 +55,21 @@ template <class C> struct GrpTe {
     typedef Fp<C> F;
     typedef te_entry_t entry_t;
     static constexpr int ENTRY_VEC = sizeof(te_entry_t) / 16;     // 9
+    typedef ted_t acc_t;                                          // FP64-pipe accumulator (te.cuh TeD)
     FP_HD static void set_inf(xyzz_t &a) { Te<C>::set_inf(a); }
 #if defined(__CUDACC__)
+    __device__ __forceinline__ static void acc_init(acc_t &a) { TeD<C>::set_inf(a); }
+    __device__ __forceinline__ static void acc_madd_staged(acc_t &acc, const uint4 *st, int stride, bool negate) {
+        te_entry_t e;
+        uint4 *t = reinterpret_cast<uint4 *>(&e);
+#pragma unroll
+        for (int k = 0; k < ENTRY_VEC; k++) t[k] = st[k * stride];
+        ted_pre_t q;
+        TeD<C>::unpack(q, e);
+        if (negate) TeD<C>::negate(q);
+        TeD<C>::madd(acc, q);
+    }
+    __device__ __noinline__ static void acc_export(xyzz_t &out, const acc_t &a) { TeD<C>::to_int(out, a); }
     __device__ __forceinline__ static void madd_staged(xyzz_t &acc, const uint4 *st, int stride, bool negate) {
         te_entry_t e;
         uint4 *t = reinterpret_cast<uint4 *>(&e);
@@ -90,7 +107,7 @@ template <class C> struct GrpTe {
     // Montgomery's trick over GRP_BATCH points: one inversion per thread.  A zero denominator (y = 0 or
     // s (x + 1) = -1: only for points outside G1, or the (0, 0) placeholder of a base flagged infinity, which the digit
     // kernel never references) is replaced by 1 so that it cannot poison its batch.
-    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t) {
+    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t, bool ark) {
         const uint32_t base = t * GRP_BATCH;
         if (base >= n) return;
         const uint32_t cnt = n - base < GRP_BATCH ? n - base : GRP_BATCH;
@@ -117,16 +134,16 @@ template <class C> struct GrpTe {
             Ec<C>::mul_ni(i1, inv, prefix[k]);
             Ec<C>::mul_ni(inv, inv, den);
             te_entry_t e;
-            Te<C>::map_finish(e, nu, nv, dv, a.y, i1);
+            Te<C>::map_finish(e, nu, nv, dv, a.y, i1, ark);
             uint4 *d = reinterpret_cast<uint4 *>(dst + base + k);
             const uint4 *s = reinterpret_cast<const uint4 *>(&e);
 #pragma unroll
             for (int v = 0; v < ENTRY_VEC; v++) d[v] = s[v];
         }
     }
-    __device__ static void entry_to_sw(fp &x, fp &y, const entry_t &e) {
+    __device__ static void entry_to_sw(fp &x, fp &y, const entry_t &e, bool ark) {
         xyzz_t a;
-        Te<C>::entry_to_point(a, e);
+        Te<C>::entry_to_point(a, e, ark);
         if (!to_sw_affine(x, y, a)) { F::set_zero(x); F::set_zero(y); }
     }
     __device__ static void load_affine_plain(affine_t &d, const affine_t *src) {
@@ -137,6 +154,23 @@ template <class C> struct GrpTe {
     }
 #endif
 };
+
+#if defined(__CUDACC__)
+// accumulator flavours of the accumulate kernel: which registers hold the running sum and which pipe multiplies
+template <class G> struct AccNative {          // the group's own integer arithmetic
+    typedef xyzz_t acc_t;
+    __device__ __forceinline__ static void init(acc_t &a) { G::set_inf(a); }
+    __device__ __forceinline__ static void madd_staged(acc_t &acc, const uint4 *st, int stride, bool negate) { G::madd_staged(acc, st, stride, negate); }
+    __device__ __forceinline__ static void export_to(xyzz_t &out, const acc_t &a) { out = a; }
+};
+template <class C> struct AccFp64Te {          // twisted Edwards on the FP64 pipe
+    typedef GrpTe<C> G;
+    typedef typename G::acc_t acc_t;
+    __device__ __forceinline__ static void init(acc_t &a) { G::acc_init(a); }
+    __device__ __forceinline__ static void madd_staged(acc_t &acc, const uint4 *st, int stride, bool negate) { G::acc_madd_staged(acc, st, stride, negate); }
+    __device__ __forceinline__ static void export_to(xyzz_t &out, const acc_t &a) { G::acc_export(out, a); }
+};
+#endif
 
 template <class C, bool TE = C::HAS_TE> struct GrpSel { typedef GrpXyzz<C> type; };
 template <class C> struct GrpSel<C, true> { typedef GrpTe<C> type; };

@@ -173,11 +173,11 @@ __global__ void __launch_bounds__(128) k_convert_points(const uint8_t *__restric
 }
 // table 0 back as arkworks (x, y) records of 96 bytes (tests)
 template <class C>
-__global__ void __launch_bounds__(128) k_export_points(const typename Grp<C>::entry_t *__restrict__ entries, uint32_t n, uint32_t *__restrict__ dst) {
+__global__ void __launch_bounds__(128) k_export_points(const typename Grp<C>::entry_t *__restrict__ entries, uint32_t n, uint32_t *__restrict__ dst, bool ark) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fp x, y;
-    Grp<C>::entry_to_sw(x, y, entries[i]);
+    Grp<C>::entry_to_sw(x, y, entries[i], ark);
     fp_abi ox, oy;
     Ec<C>::to_abi_ni(ox, x);
     Ec<C>::to_abi_ni(oy, y);
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(128) k_export_points(const typename Grp<C>::en
 }
 // short-Weierstrass affine chunk -> table entries in the curve's bucket coordinates (grp.cuh)
 template <class C>
-__global__ void __launch_bounds__(128) k_make_entries(const affine_t *__restrict__ src, uint32_t n, typename Grp<C>::entry_t *__restrict__ dst) {
-    Grp<C>::make_entries(src, n, dst, blockIdx.x * blockDim.x + threadIdx.x);
+__global__ void __launch_bounds__(128) k_make_entries(const affine_t *__restrict__ src, uint32_t n, typename Grp<C>::entry_t *__restrict__ dst, bool ark) {
+    Grp<C>::make_entries(src, n, dst, blockIdx.x * blockDim.x + threadIdx.x, ark);
 }
 // tmp[i] = 2^k * src[i]  (XYZZ, not normalised)
 template <class C>
@@ -345,7 +345,7 @@ __global__ void k_test_grp(int op, const affine_abi_t *a, const affine_abi_t *b,
     Ec<C>::from_abi_ni(sw[1][lane].x, b[srci].x); Ec<C>::from_abi_ni(sw[1][lane].y, b[srci].y);
     __syncthreads();
     // GRP_BATCH consecutive points per converting thread
-    if (lane < 64 / GRP_BATCH) { G::make_entries(sw[0], 64, ent[0], lane); G::make_entries(sw[1], 64, ent[1], lane); }
+    if (lane < 64 / GRP_BATCH) { G::make_entries(sw[0], 64, ent[0], lane, false); G::make_entries(sw[1], 64, ent[1], lane, false); }
     __syncthreads();
     if (i >= n) return;
     xyzz_t acc, other;

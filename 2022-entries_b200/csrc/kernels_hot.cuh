@@ -100,20 +100,12 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
 // The next entry (144 / 112 bytes) is fetched with 16-byte cp.async into the thread's own shared-memory slots
 // ([stage][16-byte chunk][thread]: conflict-free) while the current mixed add (~5000 integer instructions) runs, so the
 // random gather latency is hidden by one stage of prefetch.  Results go to res[piece].
-template <class C>
-__global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
-                                                           const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
-                                                           const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
-                                                           xyzz_t *__restrict__ res) {
-    typedef Grp<C> G;
-    constexpr int EV = G::ENTRY_VEC;
-    __shared__ uint4 stage[2][EV][ACC_TPB];
-    uint32_t j = blockIdx.x * ACC_TPB + threadIdx.x;
-    if (j >= *npieces_ptr) return;
-    const uint32_t piece = order[j];
-    const uint32_t start = piece_start[piece], len = piece_len[piece];
-    xyzz_t acc;
-    G::set_inf(acc);
+template <class C, class ACC>
+__device__ __forceinline__ void accumulate_piece(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+                                                 uint32_t start, uint32_t len, uint4 (*stage)[Grp<C>::ENTRY_VEC][ACC_TPB], xyzz_t *__restrict__ dst) {
+    constexpr int EV = Grp<C>::ENTRY_VEC;
+    typename ACC::acc_t acc;
+    ACC::init(acc);
     uint32_t ref = 0, ref_next = 0;
     if (len) {
         ref = __ldg(refs + start);
@@ -131,10 +123,30 @@ __global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const typename Grp<C>
         }
         cp_async_commit();
         cp_async_wait<1>();
-        G::madd_staged(acc, &stage[i & 1][0][threadIdx.x], ACC_TPB, (ref >> 31) != 0);
+        ACC::madd_staged(acc, &stage[i & 1][0][threadIdx.x], ACC_TPB, (ref >> 31) != 0);
         ref = ref_next;
     }
-    store_xyzz(res + piece, acc);
+    xyzz_t out;
+    ACC::export_to(out, acc);
+    store_xyzz(dst, out);
+}
+// FP64 = false: the group's integer arithmetic (default).  FP64 = true (curves with a twisted-Edwards model): the same
+// loop with the accumulator on the FP64 pipe (te.cuh TeD) -- measured equal to the integer flavour in this kernel
+// (both ~96 SM-clocks per mixed add at 2^26) and the two do not overlap when mixed on one SM, so
+// it is kept as an experiment switch (B200MSM_ACC=fp64), not the default.
+template <class C, bool FP64>
+__global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+                                                           const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
+                                                           const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
+                                                           xyzz_t *__restrict__ res) {
+    typedef Grp<C> G;
+    __shared__ uint4 stage[2][G::ENTRY_VEC][ACC_TPB];
+    uint32_t j = blockIdx.x * ACC_TPB + threadIdx.x;
+    if (j >= *npieces_ptr) return;
+    const uint32_t piece = order[j];
+    const uint32_t start = piece_start[piece], len = piece_len[piece];
+    if constexpr (FP64 && C::HAS_TE) accumulate_piece<C, AccFp64Te<C>>(tables, refs, start, len, stage, res + piece);
+    else accumulate_piece<C, AccNative<G>>(tables, refs, start, len, stage, res + piece);
 }
 
 }  // namespace b200msm

@@ -16,7 +16,7 @@ template <class C> struct LaunchHot {
     static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
                        int c, int W, int F, uint32_t *counters, uint32_t *refs);
     static void accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,
-                           const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res);
+                           const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res, int mix);
 };
 template <class C> struct LaunchCold {
     // n_out threads in blocks of `block` (n_out % block == 0); outT gets one entry per block
@@ -29,8 +29,8 @@ template <class C> struct LaunchCold {
     static void gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp);
     static void gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out);
     static void convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask);
-    static void export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst);
-    static void make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries);
+    static void export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst, bool ark);
+    static void make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark);
     static size_t entry_bytes();
     static void test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps);
     static void generator(fp &gx, fp &gy);      // host: the curve generator in the device representation

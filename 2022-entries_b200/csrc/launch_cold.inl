@@ -35,11 +35,11 @@ template <class C> void LaunchCold<C>::gen_scalars(cudaStream_t st, uint32_t n, 
 template <class C> void LaunchCold<C>::convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask) {
     k_convert_points<C><<<cdiv(n, 128), 128, 0, st>>>(src, n, stride, table0, infmask);
 }
-template <class C> void LaunchCold<C>::export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst) {
-    k_export_points<C><<<cdiv(n, 128), 128, 0, st>>>((const typename Grp<C>::entry_t *)entries, n, dst);
+template <class C> void LaunchCold<C>::export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst, bool ark) {
+    k_export_points<C><<<cdiv(n, 128), 128, 0, st>>>((const typename Grp<C>::entry_t *)entries, n, dst, ark);
 }
-template <class C> void LaunchCold<C>::make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries) {
-    k_make_entries<C><<<cdiv(cdiv(n, GRP_BATCH), 128), 128, 0, st>>>(src, n, (typename Grp<C>::entry_t *)dst_entries);
+template <class C> void LaunchCold<C>::make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark) {
+    k_make_entries<C><<<cdiv(cdiv(n, GRP_BATCH), 128), 128, 0, st>>>(src, n, (typename Grp<C>::entry_t *)dst_entries, ark);
 }
 template <class C> size_t LaunchCold<C>::entry_bytes() { return sizeof(typename Grp<C>::entry_t); }
 template <class C> void LaunchCold<C>::test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps) {

@@ -12,8 +12,10 @@ void LaunchHot<C>::digits(int pass, cudaStream_t st, const uint32_t *scalars, co
 }
 template <class C>
 void LaunchHot<C>::accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,
-                              const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res) {
-    k_accumulate<C><<<cdiv(max_pieces, ACC_TPB), ACC_TPB, 0, st>>>((const typename Grp<C>::entry_t *)tables, refs, order, piece_start, piece_len, npieces_ptr, res);
+                              const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res, int mix) {
+    const typename Grp<C>::entry_t *t = (const typename Grp<C>::entry_t *)tables;
+    if (mix == 0 && C::HAS_TE) k_accumulate<C, true><<<cdiv(max_pieces, ACC_TPB), ACC_TPB, 0, st>>>(t, refs, order, piece_start, piece_len, npieces_ptr, res);
+    else k_accumulate<C, false><<<cdiv(max_pieces, ACC_TPB), ACC_TPB, 0, st>>>(t, refs, order, piece_start, piece_len, npieces_ptr, res);
 }
 
 }  // namespace b200msm

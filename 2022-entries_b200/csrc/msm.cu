@@ -44,6 +44,7 @@ struct b200msm_ctx {
     uint32_t nbuckets = 0, lmax = 0, max_pieces = 0;
     uint64_t max_refs = 0;
     int launches = 0;
+    int acc_mix = 8;          // accumulate kernel flavour: 8 = integer pipe (default), 0 = FP64 pipe (B200MSM_ACC=fp64)
 
     // device memory
     uint8_t *tables = nullptr;          // T tables of n entries in the curve's bucket coordinates (grp.cuh)
@@ -218,7 +219,7 @@ template <class C> static void emit_tables(b200msm_ctx *ctx, table_scratch_t &sc
             LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[cur ^ 1]);
             cur ^= 1;
         }
-        LaunchCold<C>::make_entries(ctx->stream, sc.sw[cur], cnt, ctx->tables + ((size_t)j * ctx->n + first) * eb);
+        LaunchCold<C>::make_entries(ctx->stream, sc.sw[cur], cnt, ctx->tables + ((size_t)j * ctx->n + first) * eb, ctx->acc_mix == 0);
     }
     if (cur != 0) { affine_t *t = sc.sw[0]; sc.sw[0] = sc.sw[1]; sc.sw[1] = t; }
 }
@@ -336,7 +337,7 @@ template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_de
     launches += 6;
     cudaEventRecord(ctx->ev[3], st);
     // the hot loop
-    LaunchHot<C>::accumulate(st, ctx->max_pieces, ctx->tables, ctx->refs, ctx->order, ctx->piece_start, ctx->piece_len, npieces_ptr, ctx->res);
+    LaunchHot<C>::accumulate(st, ctx->max_pieces, ctx->tables, ctx->refs, ctx->order, ctx->piece_start, ctx->piece_len, npieces_ptr, ctx->res, ctx->acc_mix);
     launches++;
     cudaEventRecord(ctx->ev[4], st);
     // bucket reduction
@@ -384,6 +385,7 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     if (device < 0 || device >= ndev) { g_create_error = "b200msm_create: bad device index"; return -1; }
     b200msm_ctx *ctx = new b200msm_ctx();
     ctx->curve = curve; ctx->device = device; ctx->req_c = window_bits; ctx->req_tables = tables;
+    if (const char *e = getenv("B200MSM_ACC")) ctx->acc_mix = strcmp(e, "fp64") == 0 ? 0 : 8;
     ctx->entry_bytes = curve == 0 ? LaunchCold<Bls12_377>::entry_bytes() : LaunchCold<Bls12_381>::entry_bytes();
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -452,8 +454,8 @@ int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uin
     CK(cudaStreamSynchronize(ctx->stream));
     uint32_t *tmp = nullptr;
     CK(cudaMalloc((void **)&tmp, (size_t)n * 96));
-    if (ctx->curve == 0) LaunchCold<Bls12_377>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp);
-    else LaunchCold<Bls12_381>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp);
+    if (ctx->curve == 0) LaunchCold<Bls12_377>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp, ctx->acc_mix == 0);
+    else LaunchCold<Bls12_381>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp, ctx->acc_mix == 0);
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(affine96_host, tmp, (size_t)n * 96, cudaMemcpyDeviceToHost));
     cudaFree(tmp);

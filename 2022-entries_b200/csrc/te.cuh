@@ -21,10 +21,13 @@
 // Value bounds (units of p): every stored coordinate is a multiply output (< 2); the largest product below is 7 x 6.
 #pragma once
 #include "ec.cuh"
+#include "fpd.cuh"
 
 namespace b200msm {
 
-struct te_entry_t { uint32_t w[36]; };       // (y - x, y + x, 2 d x y), each 12 x 32-bit packed canonical Montgomery
+struct te_entry_t { uint32_t w[36]; };       // (y - x, y + x, 2 d x y), each a canonical value bit-packed 12 x 32.  Montgomery
+                                             // form: 2^392 for the integer accumulator (default: unpacking is bit slicing),
+                                             // 2^384 (arkworks') when the context runs the FP64-pipe accumulator
 struct te_pre_t { fp ymx, ypx, kt; };        // the same in registers
 
 template <class C> struct Te {
@@ -40,31 +43,25 @@ template <class C> struct Te {
     // the neutral element is the only point of G1 with X = 0
     FP_HD static bool is_inf(const xyzz_t &a) { return F::is_zero(a.x); }
 
-    FP_HD static void unpack(te_pre_t &q, const te_entry_t &e) {
+    // ark = false: entries hold 2^392-form values (bit slicing only); ark = true: arkworks form (one multiply each)
+    FP_HD static void unpack_one(fp &r, const uint32_t *w, bool ark) {
         fp_abi t;
 #pragma unroll
-        for (int i = 0; i < 12; i++) t.w[i] = e.w[i];
-        F::repack_from_abi(q.ymx, t);
+        for (int i = 0; i < 12; i++) t.w[i] = w[i];
+        if (ark) F::from_abi(r, t); else F::repack_from_abi(r, t);
+    }
+    FP_HD static void unpack(te_pre_t &q, const te_entry_t &e, bool ark = false) {
+        unpack_one(q.ymx, e.w, ark); unpack_one(q.ypx, e.w + 12, ark); unpack_one(q.kt, e.w + 24, ark);
+    }
+    FP_HD static void pack_one(uint32_t *w, fp v, bool ark) {
+        fp_abi t;
+        if (ark) F::to_abi(t, v); else { F::reduce(v); F::repack_to_abi(t, v); }
 #pragma unroll
-        for (int i = 0; i < 12; i++) t.w[i] = e.w[12 + i];
-        F::repack_from_abi(q.ypx, t);
-#pragma unroll
-        for (int i = 0; i < 12; i++) t.w[i] = e.w[24 + i];
-        F::repack_from_abi(q.kt, t);
+        for (int i = 0; i < 12; i++) w[i] = t.w[i];
     }
     // canonicalise (< p) and pack
-    FP_HD static void pack(te_entry_t &e, te_pre_t q) {
-        F::reduce(q.ymx); F::reduce(q.ypx); F::reduce(q.kt);
-        fp_abi t;
-        F::repack_to_abi(t, q.ymx);
-#pragma unroll
-        for (int i = 0; i < 12; i++) e.w[i] = t.w[i];
-        F::repack_to_abi(t, q.ypx);
-#pragma unroll
-        for (int i = 0; i < 12; i++) e.w[12 + i] = t.w[i];
-        F::repack_to_abi(t, q.kt);
-#pragma unroll
-        for (int i = 0; i < 12; i++) e.w[24 + i] = t.w[i];
+    FP_HD static void pack(te_entry_t &e, const te_pre_t &q, bool ark = false) {
+        pack_one(e.w, q.ymx, ark); pack_one(e.w + 12, q.ypx, ark); pack_one(e.w + 24, q.kt, ark);
     }
     // -(x, y) = (-x, y): swap the first two values, negate the third
     FP_HD static void negate(te_pre_t &q) {
@@ -133,7 +130,7 @@ template <class C> struct Te {
         E::M(den, y, dv);
     }
     // inv = 1 / den  ->  table entry
-    FP_HD static void map_finish(te_entry_t &out, const fp &nu, const fp &nv, const fp &dv, const fp &y, const fp &inv) {
+    FP_HD static void map_finish(te_entry_t &out, const fp &nu, const fp &nv, const fp &dv, const fp &y, const fp &inv, bool ark = false) {
         fp iy, idv, u, v, k;
         E::M(iy, inv, dv);                        // 1 / y
         E::M(idv, inv, y);                        // 1 / dv
@@ -145,7 +142,7 @@ template <class C> struct Te {
         load_const(k, 0);
         E::M(q.kt, u, v);
         E::M(q.kt, q.kt, k);
-        pack(out, q);
+        pack(out, q, ark);
     }
     // extended point -> short-Weierstrass affine (canonical); false for the neutral element.  One inversion.
     FP_HD static bool to_sw_affine(fp &x, fp &y, const xyzz_t &a) {
@@ -169,15 +166,78 @@ template <class C> struct Te {
         return true;
     }
     // table entry -> extended point (2x' : 2y' : 2 : .)  (tests: read the bases back)
-    FP_HD static void entry_to_point(xyzz_t &a, const te_entry_t &e) {
+    FP_HD static void entry_to_point(xyzz_t &a, const te_entry_t &e, bool ark = false) {
         te_pre_t q;
-        unpack(q, e);
+        unpack(q, e, ark);
         fp one;
         F::set_one(one);
         F::template sub<2>(a.x, q.ypx, q.ymx);
         F::add(a.y, q.ypx, q.ymx);
         F::add(a.zz, one, one);
         F::set_zero(a.zzz);                       // T is not needed by to_sw_affine
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// The same mixed addition on the FP64 pipe (fpd.cuh: 8 x 48-bit limbs in doubles, R = 2^384): the accumulate kernel's
+// inner loop on BLS12-377.  Limb growth in units of 2^48 is given per line: every multiply operand stays below 4 units
+// (2^50) and the largest value product is 7 x 6 (limit 152), so the loop needs no normalisation at all.
+struct ted_t { fpd x, y, z, t; };
+struct ted_pre_t { fpd ymx, ypx, kt; };
+
+#if defined(__CUDACC__) && defined(EC_MUL_BY_CALL)
+template <class C> __device__ __noinline__ fpd fpd_mul_call(fpd a, fpd b) { fpd r; FpD<C>::mul(r, a, b); return r; }
+#endif
+
+template <class C> struct TeD {
+    typedef FpD<C> F;
+#if defined(__CUDACC__) && defined(EC_MUL_BY_CALL)
+    __device__ __forceinline__ static void M(fpd &r, const fpd &a, const fpd &b) { r = fpd_mul_call<C>(a, b); }
+#else
+    FP_HD static void M(fpd &r, const fpd &a, const fpd &b) { F::mul(r, a, b); }
+#endif
+    FP_HD static void set_inf(ted_t &a) { F::set_zero(a.x); F::set_one(a.y); F::set_one(a.z); F::set_zero(a.t); }
+    FP_HD static void unpack(ted_pre_t &q, const te_entry_t &e) {
+        fp_abi t;
+#pragma unroll
+        for (int i = 0; i < 12; i++) t.w[i] = e.w[i];
+        F::from_abi(q.ymx, t);
+#pragma unroll
+        for (int i = 0; i < 12; i++) t.w[i] = e.w[12 + i];
+        F::from_abi(q.ypx, t);
+#pragma unroll
+        for (int i = 0; i < 12; i++) t.w[i] = e.w[24 + i];
+        F::from_abi(q.kt, t);
+    }
+    FP_HD static void negate(ted_pre_t &q) {
+        fpd t = q.ymx; q.ymx = q.ypx; q.ypx = t;
+        F::template neg<2>(q.kt, q.kt);                       // 2 units, value <= 2p
+    }
+    FP_HD static void madd(ted_t &acc, const ted_pre_t &q) {
+        fpd a, b, c, d, e, f, g, h;
+        F::template sub<3>(a, acc.y, acc.x);      // Y1 - X1          3 units   5 p
+        M(a, a, q.ymx);                           // A                1         2
+        F::add(b, acc.y, acc.x);                  // Y1 + X1          2         4
+        M(b, b, q.ypx);                           // B                1         2
+        M(c, acc.t, q.kt);                        // C                1         2     (q.kt: up to 2 units when negated)
+        F::add(d, acc.z, acc.z);                  // D = 2 Z1         2         4
+        F::template sub<3>(e, b, a);              // E = B - A        3         5
+        F::template sub<3>(f, d, c);              // F = D - C        < 4       7
+        F::add(g, d, c);                          // G = D + C        3         6
+        F::add(h, b, a);                          // H = B + A        2         4
+        M(acc.x, e, f);
+        M(acc.y, g, h);
+        M(acc.t, e, h);
+        M(acc.z, f, g);
+    }
+    // extended point in the FP64 representation -> the integer representation the reduction kernels use
+    // (14 x 28-bit, R = 2^392): through the canonical arkworks form, one multiply each way per coordinate
+    FP_HD static void to_int(xyzz_t &out, const ted_t &a) {
+        fp_abi t;
+        F::to_abi(t, a.x); Fp<C>::from_abi(out.x, t);
+        F::to_abi(t, a.y); Fp<C>::from_abi(out.y, t);
+        F::to_abi(t, a.z); Fp<C>::from_abi(out.zz, t);
+        F::to_abi(t, a.t); Fp<C>::from_abi(out.zzz, t);
     }
 };
 

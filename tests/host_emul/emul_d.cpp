@@ -1,7 +1,7 @@
 // Host build of csrc/fpd.cuh (the FP64-pipe field) with the FPU rounding toward zero (TEST ONLY).
 #include <cfenv>
 #include <cstddef>
-#include "../../2022-entries_b200/csrc/fpd.cuh"
+#include "../../2022-entries_b200/csrc/te.cuh"
 using namespace b200msm;
 typedef FpD<Bls12_377> F;
 struct rz_scope { int old; rz_scope() { old = fegetround(); fesetround(FE_TOWARDZERO); } ~rz_scope() { fesetround(old); } };
@@ -52,6 +52,38 @@ int emuld_is_zero(const void *a_, int k, int sub_form) {
     if (sub_form) { fpd y = x; F::sub<4>(x, x, y); }      // x - x + 4p: limb-dominant representation of 4p
     for (int i = 0; i < k; i++) { F::add(x, x, pp); if (i & 1) F::norm(x); }
     return F::is_zero(x) ? 1 : 0;
+}
+// FP64-pipe twisted-Edwards accumulator (te.cuh TeD): entries built by the integer map, a + reps*(+-b) accumulated in
+// the FP64 representation starting from the neutral element, exported through to_int, mapped back to short Weierstrass.
+int emuld_te_op(int op, const void *a_, const void *b_, void *out_, size_t n, int reps) {
+    rz_scope rz;
+    typedef Bls12_377 C; typedef Fp<C> FI; typedef Te<C> T; typedef TeD<C> D;
+    const affine_abi_t *a = (const affine_abi_t *)a_, *b = (const affine_abi_t *)b_; uint32_t *out = (uint32_t *)out_;
+    for (size_t i = 0; i < n; i++) {
+        te_entry_t ent[2];
+        for (int k = 0; k < 2; k++) {
+            const affine_abi_t &s = k == 0 ? a[i] : b[i];
+            fp x, y, nu, nv, dv, den, inv;
+            FI::from_abi(x, s.x); FI::from_abi(y, s.y);
+            T::map_prepare(nu, nv, dv, den, x, y);
+            FI::inv(inv, den);
+            T::map_finish(ent[k], nu, nv, dv, y, inv, true);       // arkworks-form entries: what the FP64 accumulator reads
+        }
+        ted_t acc; ted_pre_t q;
+        D::set_inf(acc);
+        D::unpack(q, ent[0]); D::madd(acc, q);
+        D::unpack(q, ent[1]);
+        if (op == 3) D::negate(q);
+        for (int k = 0; k < reps; k++) D::madd(acc, q);
+        xyzz_t r; D::to_int(r, acc);
+        fp x, y;
+        bool finite = T::to_sw_affine(x, y, r);
+        if (!finite) { FI::set_zero(x); FI::set_one(y); }
+        fp_abi ox, oy; FI::to_abi(ox, x); FI::to_abi(oy, y);
+        for (int k = 0; k < 12; k++) { out[i * 26 + k] = ox.w[k]; out[i * 26 + 12 + k] = oy.w[k]; }
+        out[i * 26 + 24] = finite ? 0 : 1; out[i * 26 + 25] = 0;
+    }
+    return 0;
 }
 void emuld_constants(uint64_t *out) {
     for (int i = 0; i < 8; i++) { out[i] = fd_p<Bls12_377>(i); out[8 + i] = fd_one<Bls12_377>(i); }

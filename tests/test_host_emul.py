@@ -205,3 +205,81 @@ def test_te_group_law(emul, oracle):
         assert np.array_equal(out[:, 96], want[:, 96]), (op, reps)
         fin = want[:, 96] == 0
         assert np.array_equal(out[fin, :96], want[fin, :96]), (op, reps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FP64-pipe field (csrc/fpd.cuh) and accumulator (te.cuh TeD), host build with the FPU rounding toward zero
+@pytest.fixture(scope="module")
+def emuld():
+    so = os.path.join(HERE, "emul_d.so")
+    src = os.path.join(HERE, "emul_d.cpp")
+    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "fpd.cuh", "ec.cuh", "te.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-frounding-math", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+    L = ctypes.CDLL(so)
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    L.emuld_fp_op.argtypes = [i32, vp, vp, vp, sz]
+    L.emuld_fp_mul_lazy.argtypes = [vp, vp, vp, sz, i32, i32]
+    L.emuld_is_zero.argtypes = [vp, i32, i32]
+    L.emuld_te_op.argtypes = [i32, vp, vp, vp, sz, i32]
+    L.emuld_constants.argtypes = [vp]
+    return L
+
+
+def test_fp64_field_constants(emuld):
+    c = np.zeros(24 + 128, np.uint64)
+    emuld.emuld_constants(_p(c))
+    p = RB.CURVES[0]["p"]
+    val = lambda a: sum(int(x) << (48 * i) for i, x in enumerate(a))
+    assert val(c[0:8]) == p and val(c[8:16]) == (1 << 384) % p
+    assert int(c[16]) == (-pow(p, -1, 1 << 48)) % (1 << 48) and int(c[17]) == pow(p, -1, 1 << 48)
+    for k in range(16):
+        row = c[24 + 8 * k: 32 + 8 * k]
+        assert val(row) == (k + 1) * p and all(int(x) >= (1 << 48) - 1 for x in row[:7])
+
+
+def test_fp64_field_ops(emuld, oracle):
+    rng = np.random.default_rng(23)
+    p = RB.CURVES[0]["p"]
+    n = 2048
+    va, vb = _rand_fp(rng, n, p), _rand_fp(rng, n, p)
+    va[:4] = [0, p - 1, 1, p - 1]
+    vb[:4] = [5, p - 1, p - 1, 0]
+    a, b = _pack(va), _pack(vb)
+    r = np.zeros_like(a)
+    for op, oop in ((0, oracle.FP_MUL), (1, oracle.FP_ADD), (2, oracle.FP_SUB), (3, oracle.FP_SQR)):
+        emuld.emuld_fp_op(op, _p(a), _p(b), _p(r), n)
+        assert np.array_equal(r.reshape(-1, 48), oracle.fp_op(oop, a, b, 0)), op
+    emuld.emuld_fp_op(4, _p(a[48:48 * 9]), _p(a[48:48 * 9]), _p(r), 8)
+    assert np.array_equal(r[:48 * 8].reshape(-1, 48), oracle.fp_op(oracle.FP_INV, a[48:48 * 9], None, 0))
+    emuld.emuld_fp_op(5, _p(a), _p(b), _p(r), n)
+    assert np.array_equal(r, a)
+    # lazy operands: (a + k1 p)(b + k2 p) with limbs up to 4 units stays normalised and below 2p (ka kb <= 152)
+    for k1, k2 in ((12, 12), (7, 6), (9, 2), (0, 0)):
+        assert emuld.emuld_fp_mul_lazy(_p(a), _p(b), _p(r), n, k1, k2) == 0
+        assert np.array_equal(r.reshape(-1, 48), oracle.fp_op(oracle.FP_MUL, a, b, 0))
+    z, nz = _pack([0]), _pack([12345])
+    for k in (0, 1, 5, 12):
+        assert emuld.emuld_is_zero(_p(z), k, 0) == 1 and emuld.emuld_is_zero(_p(z), k, 1) == 1 and emuld.emuld_is_zero(_p(nz), k, 0) == 0
+
+
+def test_fp64_te_accumulator(emuld, oracle):
+    """The accumulate kernel's inner loop arithmetic (TeD::madd chains from the neutral element, negated entries,
+    P + P, P - P) == the oracle."""
+    O = oracle
+    n = 48
+    A, B = O.gen_points(n, seed=25), O.gen_points(n, seed=29)
+    B[0] = A[0]
+    B[1] = O.aff_neg(A[1:2])[0]
+    a96, b96 = np.ascontiguousarray(A[:, :96]), np.ascontiguousarray(B[:, :96])
+    out = np.zeros((n, 104), np.uint8)
+    jacA = _jac_from_aff(O, A, 0)
+    for op, reps in ((0, 1), (0, 9), (3, 1), (3, 6), (0, 0)):
+        emuld.emuld_te_op(op, _p(a96), _p(b96), _p(out), n, reps)
+        j = jacA.copy()
+        for _ in range(reps):
+            j = O.jac_add_mixed(j, B if op == 0 else O.aff_neg(B))
+        want = O.jac_to_affine(j)
+        assert np.array_equal(out[:, 96], want[:, 96]), (op, reps)
+        fin = want[:, 96] == 0
+        assert np.array_equal(out[fin, :96], want[fin, :96]), (op, reps)
