@@ -23,6 +23,7 @@ BASES_HARNESS, BASES_DISTINCT = 0, 1
 AFFINE_BYTES, SCALAR_BYTES, PROJECTIVE_BYTES = 104, 32, 144
 PARTIAL_BYTES = 224          # one GPU's partial result: XYZZ in the device representation (4 x 14 x 28-bit limbs)
 XYZZ_ABI_BYTES = 192         # test entry points: XYZZ as 4 arkworks field elements
+ENTRY_BYTES = {BLS12_377: 144, BLS12_381: 112}      # one base-table entry in device memory (csrc/grp.cuh)
 
 _lib = None
 

@@ -153,6 +153,36 @@ __global__ void __launch_bounds__(PIECE_TPB) k_piece_order(const uint32_t *__res
 }
 
 // ---------------------------------------------------------------------------------------------
+// a5, two-level scatter (see kernels_hot.cuh k_digits_bin)
+// bin b's range of the staging array starts where its first bucket's list starts
+__global__ void __launch_bounds__(256) k_bin_init(const uint32_t *__restrict__ bucket_off, uint32_t nbuckets, int bin_shift, uint32_t nbins, uint32_t *__restrict__ bin_cursor) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbins) {
+        uint32_t first = b << bin_shift;
+        bin_cursor[b] = bucket_off[first < nbuckets ? first : nbuckets];
+    }
+}
+#define BINSC_TPB 256
+#define BINSC_EPT 8
+__global__ void __launch_bounds__(BINSC_TPB) k_bin_scatter(const uint2 *__restrict__ staging, const uint32_t *__restrict__ total_ptr,
+                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ refs) {
+    const uint32_t total = *total_ptr;
+    const size_t base = (size_t)blockIdx.x * (BINSC_TPB * BINSC_EPT);
+    if (base >= total) return;
+    uint2 v[BINSC_EPT];
+#pragma unroll
+    for (int k = 0; k < BINSC_EPT; k++) {
+        size_t idx = base + (size_t)k * BINSC_TPB + threadIdx.x;          // coalesced 8-byte loads
+        v[k] = idx < total ? __ldcs(staging + idx) : make_uint2(0xffffffffu, 0);
+    }
+    uint32_t slot[BINSC_EPT];
+#pragma unroll
+    for (int k = 0; k < BINSC_EPT; k++) slot[k] = v[k].x != 0xffffffffu ? atomicAdd(&cursor[v[k].x], 1u) : 0;
+#pragma unroll
+    for (int k = 0; k < BINSC_EPT; k++) if (v[k].x != 0xffffffffu) refs[slot[k]] = v[k].y;
+}
+
+// ---------------------------------------------------------------------------------------------
 // a11 (curve-independent part)
 // replicate the first `have` entries of a table (vec 16-byte chunks each) up to n (vector doubling, as the reference
 // generator does)

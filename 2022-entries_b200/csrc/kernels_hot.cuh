@@ -56,13 +56,9 @@ template <class C> struct ScalarOps {
     }
 };
 
-template <class C, int PASS>
-__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
-                                                uint32_t n, uint32_t table_stride, int c, int W, int F,
-                                                uint32_t *__restrict__ counters, uint32_t *__restrict__ refs) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (infmask[i >> 5] & (1u << (i & 31))) return;       // base at infinity contributes nothing
+// walks the signed digits of scalar i: fn(bucket key, point reference) for every non-zero digit
+template <class C, class FN>
+__device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scalars, uint32_t i, uint32_t table_stride, int c, int W, int F, FN fn) {
     uint32_t s[9];
     {
         const uint4 *p = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
@@ -84,13 +80,79 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
         if (flip) d = (1u << c) - d;
         carry = flip ? 1u : 0u;
         if (d == 0) continue;
-        uint32_t key = (uint32_t)(w % F) * half + d - 1;
+        fn((uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + i) | ((neg != flip) ? 0x80000000u : 0u));
+    }
+}
+
+template <class C, int PASS>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
+                                                uint32_t n, uint32_t table_stride, int c, int W, int F,
+                                                uint32_t *__restrict__ counters, uint32_t *__restrict__ refs) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (infmask[i >> 5] & (1u << (i & 31))) return;       // base at infinity contributes nothing
+    for_each_digit<C>(scalars, i, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
         if (PASS == 0) {
             atomicAdd(&counters[key], 1u);
         } else {
             uint32_t slot = atomicAdd(&counters[key], 1u);
-            refs[slot] = ((uint32_t)(w / F) * table_stride + i) | ((neg != flip) ? 0x80000000u : 0u);
+            refs[slot] = ref;
         }
+    });
+}
+
+// Two-level scatter for large problems (a5; stands in for yrrid's partition1024 / partition4096 pair,
+// Partition1024.cu:157-243, Partition4096.cu:352-433).  A direct scatter of W*n references over a 3 GB list array is
+// one 32-byte sector read-modify-write in DRAM per 4-byte reference.  Instead:
+//   k_digits_bin   groups (key, ref) pairs by bin = key >> bin_shift (<= 256 bins, each bin's share of the list array
+//                  sized to stay L2-resident): per block, count per bin in shared memory, reserve the block's range in
+//                  every bin with one global atomic per bin, then write the pairs (8 bytes each, ~W*256/bins
+//                  consecutive pairs per bin per block);
+//   k_bin_scatter  streams the pairs in order and does the atomic-slot scatter; all blocks in flight work inside one or
+//                  two bins, so cursors and list sectors are hit in L2 and reach DRAM once, as full sectors.
+#define BIN_MAX 256
+#define BIN_TPB 256
+#define BIN_ITEMS_MAX (BIN_TPB * 16)      // the staged path needs W <= 16 (it is only used for large n, where c >= 16)
+template <class C>
+__global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
+                                                        uint32_t n, uint32_t table_stride, int c, int W, int F, int bin_shift, uint32_t nbins,
+                                                        uint32_t *__restrict__ bin_cursor, uint2 *__restrict__ staging) {
+    __shared__ uint32_t cnt[BIN_MAX], start[BIN_MAX], base[BIN_MAX];
+    __shared__ uint32_t scan[BIN_TPB];
+    __shared__ uint2 sorted[BIN_ITEMS_MAX];                     // this block's pairs grouped by bin (32 KB)
+    for (uint32_t b = threadIdx.x; b < BIN_MAX; b += BIN_TPB) cnt[b] = 0;
+    __syncthreads();
+    uint32_t i = blockIdx.x * BIN_TPB + threadIdx.x;
+    const bool live = i < n && !(infmask[i >> 5] & (1u << (i & 31)));
+    if (live) for_each_digit<C>(scalars, i, table_stride, c, W, F, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> bin_shift], 1u); });
+    __syncthreads();
+    // exclusive scan of the per-bin counts (BIN_MAX == BIN_TPB: one bin per thread) and one global reservation per bin
+    {
+        const uint32_t k = cnt[threadIdx.x];
+        scan[threadIdx.x] = k;
+        __syncthreads();
+        for (int o = 1; o < BIN_TPB; o <<= 1) {
+            uint32_t t = threadIdx.x >= (uint32_t)o ? scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            scan[threadIdx.x] += t;
+            __syncthreads();
+        }
+        start[threadIdx.x] = scan[threadIdx.x] - k;
+        base[threadIdx.x] = (k && threadIdx.x < nbins) ? atomicAdd(&bin_cursor[threadIdx.x], k) : 0;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const uint32_t total = scan[BIN_TPB - 1];
+    if (live) for_each_digit<C>(scalars, i, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
+        const uint32_t b = key >> bin_shift;
+        sorted[start[b] + atomicAdd(&cnt[b], 1u)] = make_uint2(key, ref);
+    });
+    __syncthreads();
+    // consecutive threads write consecutive pairs of a bin's run: ~W*256/bins pairs (x 8 bytes) per run
+    for (uint32_t k = threadIdx.x; k < total; k += BIN_TPB) {
+        const uint2 v = sorted[k];
+        const uint32_t b = v.x >> bin_shift;
+        staging[base[b] + (k - start[b])] = v;
     }
 }
 

@@ -15,6 +15,8 @@ struct fin_args_t { fin_term_t term[FIN_MAX_TERMS]; int nterms; int F; int c; };
 template <class C> struct LaunchHot {
     static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
                        int c, int W, int F, uint32_t *counters, uint32_t *refs);
+    static void digits_bin(cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
+                           int c, int W, int F, int bin_shift, uint32_t nbins, uint32_t *bin_cursor, void *staging);
     static void accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,
                            const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res, int mix);
 };

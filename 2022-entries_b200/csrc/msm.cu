@@ -53,6 +53,10 @@ struct b200msm_ctx {
     uint32_t *counts = nullptr, *bucket_off = nullptr, *cursor = nullptr, *piece_off = nullptr;
     uint32_t *piece_start = nullptr, *piece_len = nullptr, *order = nullptr, *len_hist = nullptr, *len_cursor = nullptr;
     uint32_t *scan_tmp = nullptr, *refs = nullptr;
+    uint32_t *bin_cursor = nullptr;     // two-level scatter (large problems only)
+    uint2 *staging = nullptr;
+    int bin_shift = 0;
+    uint32_t nbins = 0;
     xyzz_t *res = nullptr, *red_buf = nullptr, *part_xyzz = nullptr;
     uint8_t *scal_buf[2] = {nullptr, nullptr};
     uint8_t *out_dev = nullptr;      // batches x 144
@@ -73,10 +77,10 @@ struct b200msm_ctx {
     }
     void free_plan() {
         void *ptrs[] = {tables, infmask, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
-                        scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1]};
+                        scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1], bin_cursor, staging};
         for (void *p : ptrs) if (p) cudaFree(p);
         tables = nullptr; infmask = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
-        scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr;
+        scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
         red_steps.clear();
         n = 0;
     }
@@ -148,6 +152,18 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     CK(dmalloc(&ctx->refs, (size_t)ctx->max_refs + 1));
     CK(dmalloc(&ctx->res, (size_t)ctx->max_pieces));
     CK(dmalloc(&ctx->part_xyzz, 1));
+    // two-level scatter when the list array is far beyond L2: bins of <= 24 MB of list each, at most BIN_MAX bins
+    ctx->nbins = 0;
+    if (ctx->max_refs * 4 > (512ull << 20) && ctx->W <= 16 && !getenv("B200MSM_DIRECT_SCATTER")) {
+        uint64_t want = (ctx->max_refs * 4 + (24ull << 20) - 1) / (24ull << 20);       // bins needed
+        int lg_nb = 0; while ((1ull << lg_nb) < nb) lg_nb++;
+        int lg_bins = 0; while ((1ull << lg_bins) < want && lg_bins < 8) lg_bins++;
+        if (lg_bins > lg_nb) lg_bins = lg_nb;
+        ctx->bin_shift = lg_nb - lg_bins;
+        ctx->nbins = (uint32_t)((nb + (1u << ctx->bin_shift) - 1) >> ctx->bin_shift);
+        CK(dmalloc(&ctx->bin_cursor, (size_t)ctx->nbins + 1));
+        CK(dmalloc(&ctx->staging, (size_t)ctx->max_refs + 1));
+    }
 
     // bucket-reduction plan (see k_reduce_slices): sizes first, then carve red_buf
     struct lvl { uint32_t n_in, m, n_out, block, nT; };
@@ -321,7 +337,14 @@ template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_de
     k_scan_block_sums<0><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp);
     k_scan_top<<<1, 1024, 0, st>>>(ctx->scan_tmp, sblocks);
     k_scan_apply<0><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, ctx->bucket_off, ctx->cursor);
-    LaunchHot<C>::digits(1, st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->cursor, ctx->refs);
+    if (ctx->nbins > 1) {
+        k_bin_init<<<cdiv(ctx->nbins, 256), 256, 0, st>>>(ctx->bucket_off, nb, ctx->bin_shift, ctx->nbins, ctx->bin_cursor);
+        LaunchHot<C>::digits_bin(st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->bin_shift, ctx->nbins, ctx->bin_cursor, ctx->staging);
+        k_bin_scatter<<<cdiv(ctx->max_refs, BINSC_TPB * BINSC_EPT), BINSC_TPB, 0, st>>>(ctx->staging, ctx->bucket_off + nb, ctx->cursor, ctx->refs);
+        launches += 2;
+    } else {
+        LaunchHot<C>::digits(1, st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->cursor, ctx->refs);
+    }
     launches += 4;
     cudaEventRecord(ctx->ev[2], st);
     // pieces

@@ -295,22 +295,22 @@ def main():
         acc_ms = stage_avg["accumulate"]
         alg_bytes = n_local * 128
         achieved = alg_bytes / (acc_ms / 1e3) / 1e9
-        # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (10 modmul: 8 mul x 378 + 2 sqr x 301) vs the
+        # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (twisted-Edwards unified add: 7 multiplies x 378) vs the
         # measured IMAD.WIDE.U32 rate: 32 lanes / clk / SM -- the fmaheavy pipe is 89 % busy when the multiplier
         # microbenchmark sustains 378 IMAD.WIDE per 13.2 SM-clocks (profiles/r01_mul_bench.txt)
         madds = info["windows"] * n_local
-        imad_per_madd = 8 * 378 + 2 * 301
+        imad_per_madd = 7 * 378
         sm_mhz = clocks["sm_mhz"] or 1965
         int_peak = 32.0 * 148 * sm_mhz * 1e6
         int_ach = madds * imad_per_madd / (acc_ms / 1e3)
         line = {
             "metric": METRIC.format(lg=lg), "value": n / (ms_dev / 1e3), "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 limbs (377-bit modular integer, 14 x 28-bit reduced radix)", "data": "synthetic",
+            "dtype": "u32 (377-bit modular integers as 14 x 28-bit limbs, IMAD.WIDE into u64 columns)", "data": "synthetic",
             "config": {"workload": f"BLS12-377 G1 MSM 2^{lg}, one batch, bases resident (harness generator shape: 2^15 distinct points replicated), uniform 253-bit scalars",
                        "log_n": lg, "points_per_gpu": n_local, "parallelism": f"point-shard x{world}" if world > 1 else "single GPU",
                        "window_bits": info["window_bits"], "windows": info["windows"], "tables": info["tables"], "folded_windows": info["folded_windows"],
-                       "buckets": info["buckets"], "l2": "inputs larger than L2 (scalars %.1f GB, base tables %.1f GB per GPU)" % (n_local * 32 / 1e9, info["tables"] * n_local * 112 / 1e9),
+                       "buckets": info["buckets"], "l2": "inputs larger than L2 (scalars %.1f GB, base tables %.1f GB per GPU)" % (n_local * 32 / 1e9, info["tables"] * n_local * M.ENTRY_BYTES[M.BLS12_377] / 1e9),
                        "init_s": round(t_init, 2), "checked": "bit-exact vs CPU oracle (closed form over known discrete logs) before timing"},
             "stages_ms": {k: round(v, 3) for k, v in stage_avg.items()},
             "roofline": {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

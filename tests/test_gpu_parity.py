@@ -199,8 +199,7 @@ def test_generated_bases_match_closed_form_2pow20(M, oracle):
     import torch
     import known_answer as KA
     O = oracle
-    n = 1 << 20
-    for mode, distinct in ((0, 1 << 15), (1, 0)):
+    for mode, distinct, n in ((0, 1 << 15, 1 << 24), (1, 0, 1 << 20)):     # 2^24: the two-level scatter path (lists > 512 MB)
         eng = M.Engine(0)
         eng.set_bases_generated(n, seed=77, mode=mode, distinct=max(distinct, 1))
         sc = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
