@@ -14,7 +14,7 @@
 //   value(a) = sum_i a.l[i] * 2^(28 i).  "Normalised": l[0..12] < 2^28 (l[13] holds whatever is left).
 //   Montgomery form x~ = x * 2^392 mod p.  The arkworks ABI uses 6 x u64 with R = 2^384; abi_to_fp / fp_to_abi convert
 //   (bit repack + one multiply by 2^400 resp. 2^384), once per base at table build and once per result.
-//   mul(a, b): limbs of a and b below 2^30 (normalised inputs, or sums of up to four normalised values), and
+//   mul(a, b): NORMALISED operands (mul_karatsuba below; mul_schoolbook also takes limbs up to 2^30), and
 //   value(a) * value(b) < 2^392 * p  (i.e. ka * kb < 2^15 for BLS12-377, 2^11 for BLS12-381 when a < ka p, b < kb p);
 //   result normalised, value < 2p.  The 11-15 spare bits make every bound in ec.cuh hold without value reductions.
 //   sub<K>(a, b) = a + K p - b limb-wise, K p stored "limb-dominant" (every limb >= 2^28 - 1) so no limb goes
@@ -212,7 +212,7 @@ template <class C> struct Fp {
     // Montgomery product a*b / 2^392 mod p (normalised, value < 2p under the bounds in the header comment).
     // Row i: t += a * b_i (14 IMAD.WIDE, no carries);  m = -t_0 / p mod 2^28;  t += m * p  (14 more; p_0 = 1 on BLS12-377
     // costs nothing);  t_0 is now a multiple of 2^28: push t_0 >> 28 into t_1 and rename the columns down by one.
-    FP_HD static void mul(fp &r, const fp &a, const fp &b) {
+    FP_HD static void mul_schoolbook(fp &r, const fp &a, const fp &b) {
         uint64_t t[N];
 #pragma unroll
         for (int i = 0; i < N; i++) {
@@ -244,6 +244,62 @@ template <class C> struct Fp {
             r.l[N - 2] = (uint32_t)v & FP_MASK;
             r.l[N - 1] = (uint32_t)(v >> FP_BITS);
         }
+    }
+    // The same product with one level of Karatsuba on a * b (a = a0 + a1 2^196, 7 limbs each):
+    //   z0 = a0 b0, z2 = a1 b1, z1 = (a0 + a1)(b0 + b1) - z0 - z2   -- 3 x 49 = 147 IMAD.WIDE instead of 196,
+    // then the 14 Montgomery rounds on the 28 columns (182): 329 against 378.  (A second level, 7 = 4 + 3, reaches 305
+    // but its extra live columns cost more in spills than the 24 multiplies save: 235 vs 228 ms at 2^26.)  The kernel is bound by the integer
+    // multiply pipe (32 IMAD.WIDE lanes/clk/SM) while the ALU pipe is a quarter busy, so trading 49 multiplies for ~90
+    // 64-bit adds is a net gain.  Needs NORMALISED operands (limbs 0..12 below 2^28, top limb below 2^27): the half
+    // sums are then below 2^29, a middle column below 7 * 2^58, and every identity holds per column (all column values
+    // are sums of non-negative products, so z1's columns never go negative).
+    FP_HD static void mul(fp &r, const fp &a, const fp &b) { mul_karatsuba(r, a, b); }
+    FP_HD static void mul_karatsuba(fp &r, const fp &a, const fp &b) {
+        constexpr int H = N / 2;      // 7
+        uint64_t t[2 * N];
+        uint64_t mid[2 * H - 1];
+        uint32_t sa[H], sb[H];
+#pragma unroll
+        for (int i = 0; i < H; i++) { sa[i] = a.l[i] + a.l[H + i]; sb[i] = b.l[i] + b.l[H + i]; }
+#pragma unroll
+        for (int k = 0; k < 2 * N; k++) t[k] = 0;
+        // z0 -> columns 0..12, z2 -> columns 14..26, middle product -> mid
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+#pragma unroll
+            for (int j = 0; j < H; j++) {
+                if (i == 0 || j == H - 1) {
+                    t[i + j] = (uint64_t)a.l[i] * b.l[j];
+                    t[N + i + j] = (uint64_t)a.l[H + i] * b.l[H + j];
+                    mid[i + j] = (uint64_t)sa[i] * sb[j];
+                } else {
+                    t[i + j] += (uint64_t)a.l[i] * b.l[j];
+                    t[N + i + j] += (uint64_t)a.l[H + i] * b.l[H + j];
+                    mid[i + j] += (uint64_t)sa[i] * sb[j];
+                }
+            }
+        }
+        // z1 = mid - z0 - z2 (per column), added at column offset 7
+#pragma unroll
+        for (int k = 0; k < 2 * H - 1; k++) mid[k] -= t[k] + t[N + k];
+#pragma unroll
+        for (int k = 0; k < 2 * H - 1; k++) t[H + k] += mid[k];
+        // Montgomery reduction of the 28 columns
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint32_t m = opaque32(((uint32_t)t[i] * C::INV) & FP_MASK);
+#pragma unroll
+            for (int j = 0; j < N; j++) t[i + j] += (uint64_t)m * C::p(j);
+            t[i + 1] += t[i] >> FP_BITS;
+        }
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < N - 1; j++) {
+            uint64_t v = t[N + j] + c;
+            r.l[j] = (uint32_t)v & FP_MASK;
+            c = v >> FP_BITS;
+        }
+        r.l[N - 1] = (uint32_t)(t[2 * N - 1] + c);
     }
     // a^2: the 91 cross products are taken once against the doubled operand (limbs of a below 2^29 here)
     FP_HD static void sqr(fp &r, const fp &a) {

@@ -13,7 +13,11 @@ template <int MODE, int TPB> __global__ void __launch_bounds__(TPB) k(uint32_t *
     a.w[11] &= 0xffffff; b.w[11] &= 0xffffff;
     if (MODE == 0) {
         fp x, y; Fp<Bls12_377>::repack_from_abi(x, a); Fp<Bls12_377>::repack_from_abi(y, b);
-        for (int it = 0; it < ITERS; it++) { Fp<Bls12_377>::mul(x, x, y); Fp<Bls12_377>::mul(y, y, x); }
+        for (int it = 0; it < ITERS; it++) { Fp<Bls12_377>::mul_schoolbook(x, x, y); Fp<Bls12_377>::mul_schoolbook(y, y, x); }
+        Fp<Bls12_377>::repack_to_abi(a, x); Fp<Bls12_377>::repack_to_abi(b, y);
+    } else if (MODE == 6) {
+        fp x, y; Fp<Bls12_377>::repack_from_abi(x, a); Fp<Bls12_377>::repack_from_abi(y, b);
+        for (int it = 0; it < ITERS; it++) { Fp<Bls12_377>::mul_karatsuba(x, x, y); Fp<Bls12_377>::mul_karatsuba(y, y, x); }
         Fp<Bls12_377>::repack_to_abi(a, x); Fp<Bls12_377>::repack_to_abi(b, y);
     } else if (MODE == 1) {
         fpd x, y; FpD<Bls12_377>::from_abi(x, a); FpD<Bls12_377>::from_abi(y, b);
@@ -56,10 +60,9 @@ int main() {
     uint32_t *io; cudaMalloc(&io, 65536); cudaMemset(io, 0x5a, 65536);
     for (int b : {1, 2, 4}) {
         run<0, 128>("integer 14x28 (IMAD.WIDE)", b, io);
+        run<6, 128>("integer 14x28 Karatsuba (329 IMAD)", b, io);
         run<1, 128>("fp64 8x48 (DFMA)", b, io);
-        run<3, 384>("mix 1 int : 1 fp64 warps (x3 TPB)", b, io);
         run<4, 384>("mix 1 int : 2 fp64 warps (x3 TPB)", b, io);
-        run<5, 384>("mix 1 int : 3 fp64 warps (x3 TPB)", b, io);
     }
     return 0;
 }

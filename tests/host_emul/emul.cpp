@@ -20,6 +20,7 @@ template <class C> static void fp_ops(int op, const fp_abi *a, const fp_abi *b, 
         case 2: F::template sub<2>(t, x, y); break;
         case 3: F::sqr(t, x); break;
         case 4: F::inv(t, x); break;
+        case 6: F::mul_karatsuba(t, x, y); break;
         default: t = x;                       // 5: ABI round trip
         }
         F::to_abi(r[i], t);
