@@ -295,11 +295,11 @@ def main():
         acc_ms = stage_avg["accumulate"]
         alg_bytes = n_local * 128
         achieved = alg_bytes / (acc_ms / 1e3) / 1e9
-        # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (twisted-Edwards unified add: 7 multiplies x 378) vs the
+        # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (twisted-Edwards unified add: 7 multiplies x 329) vs the
         # measured IMAD.WIDE.U32 rate: 32 lanes / clk / SM -- the fmaheavy pipe is 89 % busy when the multiplier
         # microbenchmark sustains 378 IMAD.WIDE per 13.2 SM-clocks (profiles/r01_mul_bench.txt)
         madds = info["windows"] * n_local
-        imad_per_madd = 7 * 378
+        imad_per_madd = 7 * 329                  # one-level Karatsuba multiplier (fp.cuh)
         sm_mhz = clocks["sm_mhz"] or 1965
         int_peak = 32.0 * 148 * sm_mhz * 1e6
         int_ach = madds * imad_per_madd / (acc_ms / 1e3)
