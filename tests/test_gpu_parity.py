@@ -269,3 +269,36 @@ def test_bucket_coordinate_system_matches_oracle(M, oracle, curve):
         assert np.array_equal(got[:, 96], want[:, 96]), (curve, op, reps)
         fin = want[:, 96] == 0
         assert np.array_equal(got[fin, :96], want[fin, :96]), (curve, op, reps)
+
+
+def test_full_size_2pow26_closed_form_and_linearity(M, oracle):
+    """BASELINE.json's headline size through size-independent properties: (1) bases k_i G with known k_i give
+    (sum s_i k_i mod r) G; (2) linearity: MSM(s) + MSM(t) == MSM(s + t mod r) for a second scalar set t = s with
+    every scalar shifted by one (so MSM(t) = MSM(s) + sum P_i, and sum P_i is itself the closed form of all-ones)."""
+    import torch
+    import known_answer as KA
+    O = oracle
+    n = 1 << 26
+    r = O.constants(0)["r"]
+    eng = M.Engine(0)
+    eng.set_bases_generated(n, seed=77, mode=0, distinct=1 << 15)
+    sc = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    eng.generate_scalars(sc.data_ptr(), n, 5)
+    out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    eng.msm_device(sc.data_ptr(), n, out.data_ptr())
+    eng.sync()
+    logs = KA.base_logs(n, 77, 0, 1 << 15)
+    t = KA.dot_mod_r(sc.cpu().numpy().reshape(n, 32), logs, r)
+    assert np.array_equal(O.jac_to_affine(out.cpu().numpy())[0], KA.expected_affine(O, 0, t))
+    # all-ones scalars: sum of the bases
+    ones = torch.zeros(n, 32, dtype=torch.uint8, device="cuda")
+    ones[:, 0] = 1
+    out1 = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    eng.msm_device(ones.data_ptr(), n, out1.data_ptr())
+    eng.sync()
+    t1 = int(np.sum(logs.astype(object))) % r
+    assert np.array_equal(O.jac_to_affine(out1.cpu().numpy())[0], KA.expected_affine(O, 0, t1))
+    # MSM(s) + MSM(1) == (t + t1) G  (group law on the two GPU results, checked by the oracle)
+    both = O.jac_add(out.cpu().numpy().reshape(1, 144), out1.cpu().numpy().reshape(1, 144))
+    assert np.array_equal(O.jac_to_affine(both)[0], KA.expected_affine(O, 0, (t + t1) % r))
+    eng.close()
