@@ -197,7 +197,7 @@ __device__ __forceinline__ void accumulate_piece(const typename Grp<C>::entry_t 
 // (both ~96 SM-clocks per mixed add at 2^26) and the two do not overlap when mixed on one SM, so
 // it is kept as an experiment switch (B200MSM_ACC=fp64), not the default.
 template <class C, bool FP64>
-__global__ void __launch_bounds__(ACC_TPB, 3) k_accumulate(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+__global__ void __launch_bounds__(ACC_TPB, ACC_MINB) k_accumulate(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
                                                            const uint32_t *__restrict__ order, const uint32_t *__restrict__ piece_start,
                                                            const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
                                                            xyzz_t *__restrict__ res) {

@@ -10,7 +10,12 @@ namespace b200msm {
 struct fin_term_t { const xyzz_t *arr; uint32_t n; uint32_t stride_f; uint32_t shift; uint32_t kind; };
 struct fin_args_t { fin_term_t term[FIN_MAX_TERMS]; int nterms; int F; int c; };
 #define NORM_BATCH 16
+#ifndef ACC_TPB
 #define ACC_TPB 128
+#endif
+#ifndef ACC_MINB
+#define ACC_MINB 3
+#endif
 
 template <class C> struct LaunchHot {
     static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
