@@ -29,7 +29,8 @@ template <class C> __device__ __forceinline__ void block_tree_sum(xyzz_t &v, xyz
 }
 template <class C, bool INDIRECT>
 __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const uint32_t *__restrict__ piece_off, uint32_t m,
-                                                       xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT) {
+                                                       xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT,
+                                                       uint32_t nchunks, size_t res_stride, size_t poff_stride) {
     __shared__ xyzz_t sh[64];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the outputs exactly
     xyzz_t run, tot, b;
@@ -38,9 +39,12 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
     for (uint32_t jj = m; jj-- > 0;) {
         uint32_t k = t * m + jj;
         if (jj + 1 < m) Grp<C>::add_ni(tot, run);                   // after the loop: tot = sum_j j * B_j
-        if (INDIRECT) {
-            uint32_t p0 = piece_off[k], p1 = piece_off[k + 1];
-            for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, in + q); Grp<C>::add_ni(run, b); }
+        if (INDIRECT) {        // a bucket = the sum of its pieces, over every chunk the point set was accumulated in
+            for (uint32_t ch = 0; ch < nchunks; ch++) {
+                const uint32_t *po = piece_off + ch * poff_stride;
+                uint32_t p0 = po[k], p1 = po[k + 1];
+                for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, in + ch * res_stride + q); Grp<C>::add_ni(run, b); }
+            }
         } else {
             load_xyzz(b, in + k);
             Grp<C>::add_ni(run, b);

@@ -56,9 +56,10 @@ template <class C> struct ScalarOps {
     }
 };
 
-// walks the signed digits of scalar i: fn(bucket key, point reference) for every non-zero digit
+// walks the signed digits of scalar i (the scalar of base number gi): fn(bucket key, point reference) for every
+// non-zero digit
 template <class C, class FN>
-__device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scalars, uint32_t i, uint32_t table_stride, int c, int W, int F, FN fn) {
+__device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scalars, uint32_t i, uint32_t gi, uint32_t table_stride, int c, int W, int F, FN fn) {
     uint32_t s[9];
     {
         const uint4 *p = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
@@ -80,18 +81,19 @@ __device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scal
         if (flip) d = (1u << c) - d;
         carry = flip ? 1u : 0u;
         if (d == 0) continue;
-        fn((uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + i) | ((neg != flip) ? 0x80000000u : 0u));
+        fn((uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + gi) | ((neg != flip) ? 0x80000000u : 0u));
     }
 }
 
 template <class C, int PASS>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
-                                                uint32_t n, uint32_t table_stride, int c, int W, int F,
+                                                uint32_t n, uint32_t first, uint32_t table_stride, int c, int W, int F,
                                                 uint32_t *__restrict__ counters, uint32_t *__restrict__ refs) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;       // scalars[i] belongs to base first + i (chunked calls)
     if (i >= n) return;
-    if (infmask[i >> 5] & (1u << (i & 31))) return;       // base at infinity contributes nothing
-    for_each_digit<C>(scalars, i, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
+    const uint32_t gi = first + i;
+    if (infmask[gi >> 5] & (1u << (gi & 31))) return;     // base at infinity contributes nothing
+    for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
         if (PASS == 0) {
             atomicAdd(&counters[key], 1u);
         } else {
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
 #define BIN_ITEMS_MAX (BIN_TPB * 16)      // the staged path needs W <= 16 (it is only used for large n, where c >= 16)
 template <class C>
 __global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
-                                                        uint32_t n, uint32_t table_stride, int c, int W, int F, int bin_shift, uint32_t nbins,
+                                                        uint32_t n, uint32_t first, uint32_t table_stride, int c, int W, int F, int bin_shift, uint32_t nbins,
                                                         uint32_t *__restrict__ bin_cursor, uint2 *__restrict__ staging) {
     __shared__ uint32_t cnt[BIN_MAX], start[BIN_MAX], base[BIN_MAX];
     __shared__ uint32_t scan[BIN_TPB];
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restri
     for (uint32_t b = threadIdx.x; b < BIN_MAX; b += BIN_TPB) cnt[b] = 0;
     __syncthreads();
     uint32_t i = blockIdx.x * BIN_TPB + threadIdx.x;
-    const bool live = i < n && !(infmask[i >> 5] & (1u << (i & 31)));
-    if (live) for_each_digit<C>(scalars, i, table_stride, c, W, F, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> bin_shift], 1u); });
+    const uint32_t gi = first + i;
+    const bool live = i < n && !(infmask[gi >> 5] & (1u << (gi & 31)));
+    if (live) for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> bin_shift], 1u); });
     __syncthreads();
     // exclusive scan of the per-bin counts (BIN_MAX == BIN_TPB: one bin per thread) and one global reservation per bin
     {
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restri
     }
     __syncthreads();
     const uint32_t total = scan[BIN_TPB - 1];
-    if (live) for_each_digit<C>(scalars, i, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
+    if (live) for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
         const uint32_t b = key >> bin_shift;
         sorted[start[b] + atomicAdd(&cnt[b], 1u)] = make_uint2(key, ref);
     });

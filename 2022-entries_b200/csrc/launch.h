@@ -18,16 +18,17 @@ struct fin_args_t { fin_term_t term[FIN_MAX_TERMS]; int nterms; int F; int c; };
 #endif
 
 template <class C> struct LaunchHot {
-    static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
+    static void digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t first, uint32_t table_stride,
                        int c, int W, int F, uint32_t *counters, uint32_t *refs);
-    static void digits_bin(cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
+    static void digits_bin(cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t first, uint32_t table_stride,
                            int c, int W, int F, int bin_shift, uint32_t nbins, uint32_t *bin_cursor, void *staging);
     static void accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,
                            const uint32_t *piece_start, const uint32_t *piece_len, const uint32_t *npieces_ptr, xyzz_t *res, int mix);
 };
 template <class C> struct LaunchCold {
     // n_out threads in blocks of `block` (n_out % block == 0); outT gets one entry per block
-    static void reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT);
+    static void reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT,
+                              uint32_t nchunks, size_t res_stride, size_t poff_stride);
     static void block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out);
     static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac);
     static void combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac);

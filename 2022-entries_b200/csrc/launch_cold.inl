@@ -5,9 +5,10 @@
 namespace b200msm {
 
 template <class C>
-void LaunchCold<C>::reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT) {
-    if (indirect) k_reduce_slices<C, true><<<n_out / block, block, 0, st>>>(in, piece_off, m, outS, outT);
-    else k_reduce_slices<C, false><<<n_out / block, block, 0, st>>>(in, nullptr, m, outS, outT);
+void LaunchCold<C>::reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT,
+                                  uint32_t nchunks, size_t res_stride, size_t poff_stride) {
+    if (indirect) k_reduce_slices<C, true><<<n_out / block, block, 0, st>>>(in, piece_off, m, outS, outT, nchunks, res_stride, poff_stride);
+    else k_reduce_slices<C, false><<<n_out / block, block, 0, st>>>(in, nullptr, m, outS, outT, 1, 0, 0);
 }
 template <class C> void LaunchCold<C>::block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out) {
     k_block_sum<C><<<ngroups, group < 128 ? group : 128, 0, st>>>(in, group, out);

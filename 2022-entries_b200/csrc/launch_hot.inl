@@ -5,15 +5,15 @@
 namespace b200msm {
 
 template <class C>
-void LaunchHot<C>::digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
+void LaunchHot<C>::digits(int pass, cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t first, uint32_t table_stride,
                           int c, int W, int F, uint32_t *counters, uint32_t *refs) {
-    if (pass == 0) k_digits<C, 0><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, table_stride, c, W, F, counters, refs);
-    else k_digits<C, 1><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, table_stride, c, W, F, counters, refs);
+    if (pass == 0) k_digits<C, 0><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, first, table_stride, c, W, F, counters, refs);
+    else k_digits<C, 1><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, first, table_stride, c, W, F, counters, refs);
 }
 template <class C>
-void LaunchHot<C>::digits_bin(cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t table_stride,
+void LaunchHot<C>::digits_bin(cudaStream_t st, const uint32_t *scalars, const uint32_t *infmask, uint32_t n, uint32_t first, uint32_t table_stride,
                               int c, int W, int F, int bin_shift, uint32_t nbins, uint32_t *bin_cursor, void *staging) {
-    k_digits_bin<C><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, table_stride, c, W, F, bin_shift, nbins, bin_cursor, (uint2 *)staging);
+    k_digits_bin<C><<<cdiv(n, 256), 256, 0, st>>>(scalars, infmask, n, first, table_stride, c, W, F, bin_shift, nbins, bin_cursor, (uint2 *)staging);
 }
 template <class C>
 void LaunchHot<C>::accumulate(cudaStream_t st, uint32_t max_pieces, const void *tables, const uint32_t *refs, const uint32_t *order,

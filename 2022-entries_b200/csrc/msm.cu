@@ -44,6 +44,9 @@ struct b200msm_ctx {
     uint32_t nbuckets = 0, lmax = 0, max_pieces = 0;
     uint64_t max_refs = 0;
     int launches = 0;
+    int chunks_alloc = 1;     // copies of piece_off / res (one per chunk of a chunked MSM)
+    int host_chunks = 0;      // msm_host: split the first batch into this many chunks (0 = by size)
+    cudaEvent_t ev_chunk[8] = {};
     int acc_mix = 8;          // accumulate kernel flavour: 8 = integer pipe (default), 0 = FP64 pipe (B200MSM_ACC=fp64)
 
     // device memory
@@ -83,6 +86,7 @@ struct b200msm_ctx {
         scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
         red_steps.clear();
         n = 0;
+        chunks_alloc = 1;
     }
 };
 
@@ -318,19 +322,24 @@ static void generator(int curve, fp &gx, fp &gy) {
 
 // ---------------------------------------------------------------------------------------------
 // one MSM on the context's stream.  scalars: device, n x 32 bytes.  Exactly one of out_jac / out_xyzz is set.
-template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz, bool hist_done) {
+// Stages 1-5 for the bases [first, first + count) with their scalars at scalars_dev: digits, grouping, accumulation into
+// this chunk's own bucket-sum array.  A plain MSM is one chunk covering everything; msm_host splits the first batch of
+// a call so that the upload of chunk k+1 overlaps the accumulation of chunk k (the reduction then sums over chunks).
+template <class C> static int run_chunk_t(b200msm_ctx *ctx, const void *scalars_dev, uint32_t first, uint32_t count, int chunk) {
     cudaStream_t st = ctx->stream;
     const uint32_t n = (uint32_t)ctx->n, nb = ctx->nbuckets, lmax = ctx->lmax;
     const uint32_t *sc = (const uint32_t *)scalars_dev;
+    uint32_t *piece_off = ctx->piece_off + (size_t)chunk * (nb + 1);
+    xyzz_t *res = ctx->res + (size_t)chunk * ctx->max_pieces;
     int launches = 0;
-    ctx->ev = ctx->evr[ctx->ev_steps % b200msm_ctx::EV_RING];
-    ctx->ev_steps++;
-    cudaEventRecord(ctx->ev[0], st);
-    if (!hist_done) {
-        CK(cudaMemsetAsync(ctx->counts, 0, ((size_t)nb + 1) * 4, st));
-        LaunchHot<C>::digits(0, st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->counts, nullptr);
-        launches++;
+    if (chunk == 0) {
+        ctx->ev = ctx->evr[ctx->ev_steps % b200msm_ctx::EV_RING];
+        ctx->ev_steps++;
+        cudaEventRecord(ctx->ev[0], st);
     }
+    CK(cudaMemsetAsync(ctx->counts, 0, ((size_t)nb + 1) * 4, st));
+    LaunchHot<C>::digits(0, st, sc, ctx->infmask, count, first, n, ctx->c, ctx->W, ctx->F, ctx->counts, nullptr);
+    launches++;
     cudaEventRecord(ctx->ev[1], st);
     // bucket offsets (and scatter cursors), then scatter the point references
     const uint32_t sblocks = cdiv(nb, SCAN_TPB * SCAN_EPT);
@@ -339,47 +348,75 @@ template <class C> static int run_msm_t(b200msm_ctx *ctx, const void *scalars_de
     k_scan_apply<0><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, ctx->bucket_off, ctx->cursor);
     if (ctx->nbins > 1) {
         k_bin_init<<<cdiv(ctx->nbins, 256), 256, 0, st>>>(ctx->bucket_off, nb, ctx->bin_shift, ctx->nbins, ctx->bin_cursor);
-        LaunchHot<C>::digits_bin(st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->bin_shift, ctx->nbins, ctx->bin_cursor, ctx->staging);
-        k_bin_scatter<<<cdiv(ctx->max_refs, BINSC_TPB * BINSC_EPT), BINSC_TPB, 0, st>>>(ctx->staging, ctx->bucket_off + nb, ctx->cursor, ctx->refs);
+        LaunchHot<C>::digits_bin(st, sc, ctx->infmask, count, first, n, ctx->c, ctx->W, ctx->F, ctx->bin_shift, ctx->nbins, ctx->bin_cursor, ctx->staging);
+        k_bin_scatter<<<cdiv((uint64_t)ctx->W * count, BINSC_TPB * BINSC_EPT), BINSC_TPB, 0, st>>>(ctx->staging, ctx->bucket_off + nb, ctx->cursor, ctx->refs);
         launches += 2;
     } else {
-        LaunchHot<C>::digits(1, st, sc, ctx->infmask, n, n, ctx->c, ctx->W, ctx->F, ctx->cursor, ctx->refs);
+        LaunchHot<C>::digits(1, st, sc, ctx->infmask, count, first, n, ctx->c, ctx->W, ctx->F, ctx->cursor, ctx->refs);
     }
     launches += 4;
     cudaEventRecord(ctx->ev[2], st);
     // pieces
     k_scan_block_sums<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp);
     k_scan_top<<<1, 1024, 0, st>>>(ctx->scan_tmp, sblocks);
-    k_scan_apply<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, ctx->piece_off, nullptr);
+    k_scan_apply<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, piece_off, nullptr);
     CK(cudaMemsetAsync(ctx->len_hist, 0, ((size_t)lmax + 1) * 4, st));
     const size_t hist_smem = ((size_t)lmax + 1) * 4;
-    k_piece_fill<<<cdiv(nb, PIECE_TPB), PIECE_TPB, hist_smem, st>>>(ctx->bucket_off, ctx->piece_off, nb, lmax, ctx->piece_start, ctx->piece_len, ctx->len_hist);
+    k_piece_fill<<<cdiv(nb, PIECE_TPB), PIECE_TPB, hist_smem, st>>>(ctx->bucket_off, piece_off, nb, lmax, ctx->piece_start, ctx->piece_len, ctx->len_hist);
     k_piece_len_scan<<<1, 1024, 0, st>>>(ctx->len_hist, lmax, ctx->len_cursor);
-    const uint32_t *npieces_ptr = ctx->piece_off + nb;
+    const uint32_t *npieces_ptr = piece_off + nb;
     k_piece_order<<<cdiv(ctx->max_pieces, PIECE_TPB), PIECE_TPB, hist_smem, st>>>(ctx->piece_len, npieces_ptr, lmax, ctx->len_cursor, ctx->order);
     launches += 6;
     cudaEventRecord(ctx->ev[3], st);
     // the hot loop
-    LaunchHot<C>::accumulate(st, ctx->max_pieces, ctx->tables, ctx->refs, ctx->order, ctx->piece_start, ctx->piece_len, npieces_ptr, ctx->res, ctx->acc_mix);
+    LaunchHot<C>::accumulate(st, ctx->max_pieces, ctx->tables, ctx->refs, ctx->order, ctx->piece_start, ctx->piece_len, npieces_ptr, res, ctx->acc_mix);
     launches++;
     cudaEventRecord(ctx->ev[4], st);
-    // bucket reduction
+    ctx->launches = (chunk == 0 ? 0 : ctx->launches) + launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+// Stages 6-7: bucket reduction over the chunks' bucket sums, window combine, export.
+template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz) {
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
     for (const red_step_t &s : ctx->red_steps) {
         if (s.kind == 2) LaunchCold<C>::block_sum(st, s.in, s.n_out, s.m, s.outS);
-        else LaunchCold<C>::reduce_slices(s.kind == 0, st, s.in, ctx->piece_off, s.n_out, s.block, s.m, s.outS, s.outT);
+        else LaunchCold<C>::reduce_slices(s.kind == 0, st, s.in, ctx->piece_off, s.n_out, s.block, s.m, s.outS, s.outT, (uint32_t)nchunks, ctx->max_pieces, (size_t)ctx->nbuckets + 1);
         launches++;
     }
     cudaEventRecord(ctx->ev[5], st);
     LaunchCold<C>::finalize(st, ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac);
     launches++;
     cudaEventRecord(ctx->ev[6], st);
-    ctx->launches = launches;
+    ctx->launches += launches;
     CK(cudaGetLastError());
     return 0;
 }
-static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz, bool hist_done = false) {
-    return ctx->curve == 0 ? run_msm_t<Bls12_377>(ctx, scalars_dev, out_jac, out_xyzz, hist_done)
-                           : run_msm_t<Bls12_381>(ctx, scalars_dev, out_jac, out_xyzz, hist_done);
+static int run_chunk(b200msm_ctx *ctx, const void *scalars_dev, uint32_t first, uint32_t count, int chunk) {
+    return ctx->curve == 0 ? run_chunk_t<Bls12_377>(ctx, scalars_dev, first, count, chunk) : run_chunk_t<Bls12_381>(ctx, scalars_dev, first, count, chunk);
+}
+static int run_reduce(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz) {
+    return ctx->curve == 0 ? run_reduce_t<Bls12_377>(ctx, nchunks, out_jac, out_xyzz) : run_reduce_t<Bls12_381>(ctx, nchunks, out_jac, out_xyzz);
+}
+// one MSM on the context's stream.  scalars: device, n x 32 bytes.  Exactly one of out_jac / out_xyzz is set.
+static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz) {
+    int rc = run_chunk(ctx, scalars_dev, 0, (uint32_t)ctx->n, 0);
+    if (rc) return rc;
+    return run_reduce(ctx, 1, out_jac, out_xyzz);
+}
+// piece_off / res hold one copy per chunk
+static int ensure_chunks(b200msm_ctx *ctx, int k) {
+    if (k <= ctx->chunks_alloc) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->piece_off); cudaFree(ctx->res);
+    ctx->piece_off = nullptr; ctx->res = nullptr;
+    CK(dmalloc(&ctx->piece_off, (size_t)k * ((size_t)ctx->nbuckets + 1)));
+    CK(dmalloc(&ctx->res, (size_t)k * ctx->max_pieces));
+    ctx->chunks_alloc = k;
+    // the reduction plan reads level 0 from ctx->res
+    for (red_step_t &s : ctx->red_steps) if (s.kind == 0) s.in = ctx->res;
+    return 0;
 }
 
 static int check_ctx(b200msm_ctx *ctx) {
@@ -409,11 +446,13 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     b200msm_ctx *ctx = new b200msm_ctx();
     ctx->curve = curve; ctx->device = device; ctx->req_c = window_bits; ctx->req_tables = tables;
     if (const char *e = getenv("B200MSM_ACC")) ctx->acc_mix = strcmp(e, "fp64") == 0 ? 0 : 8;
+    if (const char *e = getenv("B200MSM_HOST_CHUNKS")) ctx->host_chunks = atoi(e);
     ctx->entry_bytes = curve == 0 ? LaunchCold<Bls12_377>::entry_bytes() : LaunchCold<Bls12_381>::entry_bytes();
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int r = 0; r < b200msm_ctx::EV_RING; r++) for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->evr[r][i]);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming); }
     if (e != cudaSuccess) {
         g_create_error = std::string("b200msm_create: ") + cudaGetErrorString(e);
@@ -431,6 +470,7 @@ int b200msm_destroy(b200msm_ctx *ctx) {
     ctx->free_plan();
     if (ctx->out_dev) cudaFree(ctx->out_dev);
     for (auto &row : ctx->evr) for (auto &e : row) if (e) cudaEventDestroy(e);
+    for (auto &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -528,8 +568,32 @@ int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uin
     // the caller's stream may hold earlier work on these buffers
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
     CK(cudaEventRecord(ctx->ev_free[1], ctx->stream));
+    // The upload of batch b+1 overlaps the compute of batch b.  Nothing hides the upload of the FIRST batch, so that
+    // batch is split into chunks of bases: chunk k+1 uploads while chunk k accumulates (each chunk into its own
+    // bucket sums, one shared reduction at the end).  Stands in for the 1/4 + 3/4 split of the reference's fastest
+    // entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).
+    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : 1);
+    if (nch > 8) nch = 8;
+    if ((uint64_t)nch > n) nch = 1;
+    if (nch > 1) { rc = ensure_chunks(ctx, nch); if (rc) return rc; }
     for (uint64_t b = 0; b < batches; b++) {
         int k = (int)(b & 1);
+        if (b == 0 && nch > 1) {
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[k], 0));
+            const uint64_t per = (n + nch - 1) / nch;
+            for (int ch = 0; ch < nch; ch++) {
+                const uint64_t first = (uint64_t)ch * per, cnt = first + per <= n ? per : n - first;
+                CK(cudaMemcpyAsync(ctx->scal_buf[k] + first * 32, (const uint8_t *)scalars_host + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CK(cudaEventRecord(ctx->ev_chunk[ch], ctx->copy_stream));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[ch], 0));
+                rc = run_chunk(ctx, ctx->scal_buf[k] + first * 32, (uint32_t)first, (uint32_t)cnt, ch);
+                if (rc) return rc;
+            }
+            rc = run_reduce(ctx, nch, ctx->out_dev, nullptr);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->ev_free[k], ctx->stream));
+            continue;
+        }
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[k], 0));
         CK(cudaMemcpyAsync(ctx->scal_buf[k], (const uint8_t *)scalars_host + b * bytes, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));

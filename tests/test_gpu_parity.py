@@ -302,3 +302,25 @@ def test_full_size_2pow26_closed_form_and_linearity(M, oracle):
     both = O.jac_add(out.cpu().numpy().reshape(1, 144), out1.cpu().numpy().reshape(1, 144))
     assert np.array_equal(O.jac_to_affine(both)[0], KA.expected_affine(O, 0, (t + t1) % r))
     eng.close()
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+def test_first_batch_chunked_upload(M, oracle, monkeypatch, chunks):
+    """msm_host splits the first batch of a call into chunks of bases (upload / accumulate overlap, one shared bucket
+    reduction).  Forced here at small, ragged sizes; at 2^24 and above it is the default."""
+    O = oracle
+    monkeypatch.setenv("B200MSM_HOST_CHUNKS", str(chunks))
+    for n, batches in ((1000, 1), (1 << 12, 3), (5, 2)):
+        pts = O.gen_points(n, seed=80 + n)
+        if n > 64:
+            pts[7] = 0
+            pts[7, 96] = 1                                   # an infinity base inside a later chunk's range
+            pts[n - 3] = O.aff_neg(pts[n - 4:n - 3])[0]
+        sc = O.gen_scalars(n * batches, seed=81 + n)
+        ctx = M.multi_scalar_mult_init(pts)
+        out = M.multi_scalar_mult(ctx, pts, sc)
+        out_again = M.multi_scalar_mult(ctx, pts, sc)
+        ctx.free()
+        assert np.array_equal(out, out_again)                # canonical output: byte-identical across calls
+        for b in range(batches):
+            assert np.array_equal(O.jac_to_affine(out[b]), O.jac_to_affine(O.ark_msm(pts, sc[b * n:(b + 1) * n]))), (n, b)
