@@ -60,3 +60,28 @@ def test_bad_arguments(M):
     assert L.MSMAllocContext(0, 1) is None
     with pytest.raises(M.MsmError):
         M.multi_scalar_mult(M.MultiScalarMultContext(), np.zeros((4, 104), np.uint8), np.zeros((5, 32), np.uint8))   # length mismatch
+
+
+def build_c_harness():
+    """g++ build of tests/c_harness/msm_harness.cpp (the C++ twin of the reference's tests/msm.rs) against the two .so files."""
+    import subprocess
+    from oracle import oracle as O
+    O.build()
+    d = os.path.join(ROOT, "tests", "c_harness")
+    exe = os.path.join(d, "msm_harness")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(d, "msm_harness.cpp"), "-I" + os.path.join(ROOT, "include"),
+                           "-L" + os.path.join(ROOT, "2022-entries_b200"), "-lb200msm", "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "2022-entries_b200"), "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe])
+    return exe
+
+
+def test_c_harness_links_and_fails_loudly_without_gpu(M):
+    """The compiled-code client of the C ABI links against every symbol it uses; with no CUDA device it must stop with
+    the library's error, not compute anything."""
+    import subprocess
+    import torch
+    exe = build_c_harness()
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present: the GPU suite runs the harness for real")
+    p = subprocess.run([exe, "8"], capture_output=True, text=True)
+    assert p.returncode == 2 and "no CPU path" in p.stderr

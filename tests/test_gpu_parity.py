@@ -324,3 +324,12 @@ def test_first_batch_chunked_upload(M, oracle, monkeypatch, chunks):
         assert np.array_equal(out, out_again)                # canonical output: byte-identical across calls
         for b in range(batches):
             assert np.array_equal(O.jac_to_affine(out[b]), O.jac_to_affine(O.ark_msm(pts, sc[b * n:(b + 1) * n]))), (n, b)
+
+
+def test_c_harness(M):
+    """The C++ twin of the reference's tests/msm.rs: both ABI families from compiled code, 4 batches of 2^12 points."""
+    import subprocess
+    from test_abi_and_host import build_c_harness
+    p = subprocess.run([build_c_harness(), "12"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "msm_harness ok" in p.stdout
