@@ -326,6 +326,13 @@ def main():
         sm_mhz = clocks["sm_mhz"] or 1965
         int_peak = 32.0 * 148 * sm_mhz * 1e6
         int_ach = madds * imad_per_madd / (acc_ms / 1e3)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_accumulate"]
+            if tr["log_n"] == lg and tr["n_gpus"] == world:
+                traffic = tr["traffic_bytes"]          # dram read + write of one launch, from the committed ncu --set full capture
+        except Exception:
+            pass
         line = {
             "metric": METRIC.format(lg=lg), "value": n / (ms_dev / 1e3), "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -336,7 +343,7 @@ def main():
                        "buckets": info["buckets"], "l2": "inputs larger than L2 (scalars %.1f GB, base tables %.1f GB per GPU)" % (n_local * 32 / 1e9, info["tables"] * n_local * M.ENTRY_BYTES[M.BLS12_377] / 1e9),
                        "init_s": round(t_init, 2), "checked": "bit-exact vs CPU oracle (closed form over known discrete logs) before timing"},
             "stages_ms": {k: round(v, 3) for k, v in stage_avg.items()},
-            "roofline": {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "k_accumulate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "ms_per_launch": acc_ms, "algorithmic_bytes": alg_bytes,
                          "note": "integer-pipe bound by construction; see int_pipe"},
             "int_pipe": {"imad_wide_per_launch": madds * imad_per_madd, "achieved_per_s": int_ach, "peak_per_s": int_peak, "frac": int_ach / int_peak,
