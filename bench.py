@@ -37,13 +37,23 @@ SEED_BASES, SEED_SCALARS, DISTINCT = 77, 1234, 1 << 15
 
 
 def measured_peak_gbs():
+    """HBM copy bandwidth the driver measured on this pool (MEASURED_PEAKS.json), else the recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+
+    def find(d):
+        if isinstance(d, dict):
+            for k, v in d.items():           # e.g. {"hbm_gbs": 6451.8, ...}; tolerate nesting and unit suffixes
+                if "hbm" in str(k).lower() and isinstance(v, (int, float)) and v > 0:
+                    return float(v) * (1000.0 if v < 50 else 1.0)      # a value in TB/s
+                r = find(v)
+                if r:
+                    return r
+        return None
     try:
         with open(path) as f:
-            d = json.load(f)
-        for k in ("hbm_gbs", "hbm_copy_gbs", "hbm_gb_s"):
-            if k in d:
-                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+            v = find(json.load(f))
+        if v:
+            return v, "measured (MEASURED_PEAKS.json)"
     except Exception:
         pass
     return 6650.0, "fallback (B200_PROFILING.md)"
