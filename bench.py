@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "BLS12-377 G1 MSM 2^{lg} points/s"
+WORKLOAD = ("BLS12-377 G1 MSM 2^{lg}, one batch, bases resident (harness generator shape: 2^15 distinct points replicated), "
+            "uniform 253-bit scalars")
 SEED_BASES, SEED_SCALARS, DISTINCT = 77, 1234, 1 << 15
 
 
@@ -138,7 +140,7 @@ def run_reference(args):
     sample = f"2^{ls} points per step (harness-shaped: 2^10 distinct bases replicated, uniform scalars), arkworks window rule c={O.window_bits(1 << ls)}"
     line = {"impl": "reference", "metric": METRIC.format(lg=lg), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (377-bit modular integer)",
-            "data": "synthetic", "config": {"workload": f"BLS12-377 G1 MSM 2^{lg} (CPU arm: bounded sample of 2^{ls} points per step)", "log_n": lg},
+            "data": "synthetic", "config": {"workload": WORKLOAD.format(lg=lg), "log_n": lg, "cpu_sample_log_n": ls},
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -347,7 +349,7 @@ def main():
             "metric": METRIC.format(lg=lg), "value": n / (ms_dev / 1e3), "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 (377-bit modular integers as 14 x 28-bit limbs, IMAD.WIDE into u64 columns)", "data": "synthetic",
-            "config": {"workload": f"BLS12-377 G1 MSM 2^{lg}, one batch, bases resident (harness generator shape: 2^15 distinct points replicated), uniform 253-bit scalars",
+            "config": {"workload": WORKLOAD.format(lg=lg),
                        "log_n": lg, "points_per_gpu": n_local, "parallelism": f"point-shard x{world}" if world > 1 else "single GPU",
                        "window_bits": info["window_bits"], "windows": info["windows"], "tables": info["tables"], "folded_windows": info["folded_windows"],
                        "buckets": info["buckets"], "l2": "inputs larger than L2 (scalars %.1f GB, base tables %.1f GB per GPU)" % (n_local * 32 / 1e9, info["tables"] * n_local * M.ENTRY_BYTES[M.BLS12_377] / 1e9),
