@@ -1,14 +1,14 @@
 // fp.cuh -- base-field arithmetic for sm_100a: 14 limbs x 28 bits ("reduced radix"), Montgomery with R = 2^392.
 //
-// Why this representation (measured on B200, profiles/r01_imad_microbench.txt and
-// profiles/r01_ncu_accumulate_v1_carrychain.txt): integer multiplies issue only on the "fmaheavy" half of the FMA
-// pipe; plain IMAD.WIDE.U32 sustains 63 / clk / SM, but the carry-predicated IMAD.WIDE.U32.X that a 12 x 32-bit
-// multiplier is made of runs at exactly half that, and ptxas splits the constant-operand half of the reduction into
-// IMAD.X + IMAD.HI.U32.X pairs -- 576 heavy-pipe slots per multiply, pipe 89 % busy, issue slots 32 % busy.
-// With 28-bit limbs a column of 14 + 14 products (each < 2^60) fits a 64-bit accumulator, so the multiplier is
-// 14*14*2 - 14 = 378 plain IMAD.WIDE with NO carry flags; the little carry work left (one shift+add per round, one
-// normalisation at the end) goes to the ALU pipe, which was 11 % busy.  Stands in for yrrid MP.cu:141-367,
-// matter-labs ff_dispatch_st.cuh:234-481, sppark mont_t.cuh:353-427 (all 12 x 32-bit carry-chain multipliers).
+// Why this representation (measured on B200: profiles/r01_mul_bench.txt, profiles/r01_ncu_accumulate_*.txt): integer
+// multiplies issue only on the "fmaheavy" half of the FMA pipe, at 32 lanes (one warp instruction) per clock per SM,
+// and that pipe is what bounds the whole MSM.  A 12 x 32-bit multiplier (every reference entry) needs carry-predicated
+// IMAD.WIDE.X chains plus IMAD.HI/IMAD.X pairs for the constant-operand half -- 576 heavy-pipe slots per multiply.
+// With 28-bit limbs a column of 14 + 14 products (each < 2^56) fits a 64-bit accumulator, so the schoolbook multiplier
+// is 14*14*2 - 14 = 378 plain IMAD.WIDE with NO carry flags, and one level of Karatsuba on a * b brings it to 329
+// (mul_karatsuba below); the carry work left (one shift+add per round, one normalisation at the end, the Karatsuba
+// column sums) goes to the ALU pipe, which is a quarter busy.  Stands in for yrrid MP.cu:141-367, matter-labs
+// ff_dispatch_st.cuh:234-481, sppark mont_t.cuh:353-427 (all 12 x 32-bit carry-chain multipliers).
 //
 // Conventions
 //   value(a) = sum_i a.l[i] * 2^(28 i).  "Normalised": l[0..12] < 2^28 (l[13] holds whatever is left).

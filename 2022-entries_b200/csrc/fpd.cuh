@@ -1,18 +1,19 @@
 // fpd.cuh -- base-field arithmetic on the FP64 pipe: 8 limbs x 48 bits held in doubles, Montgomery R = 2^384.
 //
-// Why (measured on B200, profiles/r01_ncu_accumulate_v2_radix28.txt): the integer multiplier (fp.cuh) is bound by the
-// "fmaheavy" half of the FMA pipe -- IMAD.WIDE issues at one warp instruction per clock per SM (32 lanes), so 378
-// IMAD.WIDE per field multiply cost 11.8 SM-clocks per thread-multiply.  B200 (unlike B300 and the consumer parts)
-// has a full-rate FP64 pipe: DFMA at 64 lanes / clock / SM, separate from the integer pipes.  A double-precision FMA
-// with a rounding-toward-zero bias constant returns either the high or the low 48 bits of a 50 x 50-bit product exactly
+// Why (measured on B200, profiles/r01_mul_bench.txt, profiles/r01_fp64_accumulate.txt): the integer multiplier (fp.cuh)
+// is bound by the "fmaheavy" half of the FMA pipe -- IMAD.WIDE issues at 32 lanes / clock / SM.  B200 (unlike B300 and
+// the consumer parts) has a full-rate FP64 pipe: DFMA at 64 lanes / clock / SM.  A double-precision FMA with a
+// rounding-toward-zero bias constant returns either the high or the low 48 bits of a 50 x 50-bit product exactly
 // (Emmart, Zheng, Weems, "Faster modular exponentiation using double precision floating point arithmetic on the GPU",
 // ARITH 2018):
 //      hi = fma_rz(a, b, 2^100)            = 2^100 + floor(a b / 2^48) 2^48      (ulp of [2^100, 2^101) is 2^48)
 //      lo = fma_rz(a, b, 2^100 + 2^52 - hi) = 2^52 + (a b mod 2^48)               (exact: the sum fits 53 bits)
 // Both results have a FIXED exponent, so their IEEE bit patterns add as 64-bit integers (ALU pipe: IADD3 + IADD3.X)
 // and the exponent fields are cancelled by a per-column constant.  A multiply is 128 limb products x (2 DFMA + 1 DADD)
-// on the FP64 pipe and ~400 ALU instructions, against 378 IMAD.WIDE + ~260 ALU: the FP64 and ALU pipes run side by
-// side at 0.5 warp instructions / clock / scheduler each, so the bound drops from 11.8 to ~6.5 SM-clocks per multiply.
+// on the FP64 pipe and ~350 ALU instructions.  MEASURED: 10.7 SM-clocks per multiply against 13.4 for the schoolbook
+// integer multiplier and 12.1 for the Karatsuba one -- the 64-bit operand traffic makes it dispatch-bound at 59 % FP64 /
+// 48 % ALU / 56 % issue, and inside the accumulate kernel (te.cuh TeD) it ties with the integer flavour instead of
+// beating it.  It is therefore a selectable flavour (B200MSM_ACC=fp64), not the default.
 // No reference entry does this (all use 32-bit integer multipliers: yrrid MP.cu:141-367, matter-labs
 // ff_dispatch_st.cuh:234-481, sppark mont_t.cuh:353-427) -- their target GPUs (A40, sm_70..86) have 1/32-rate FP64.
 //

@@ -2,8 +2,8 @@
 //
 //   E_te:  -x^2 + y^2 = 1 + d x^2 y^2,  extended coordinates (X : Y : Z : T), x = X/Z, y = Y/Z, T = XY/Z.
 //
-// Why: the accumulate kernel is bound by the integer-multiply pipe (fmaheavy 88 % busy, profiles/
-// r01_ncu_accumulate_v3_calls.txt), so the only way down is fewer multiplies per point.  With the base tables stored as
+// Why: the accumulate kernel is bound by the integer-multiply pipe (fmaheavy 88-89 % busy, profiles/
+// r01_ncu_accumulate_v3_calls.txt, r01_ncu_accumulate_v5_te_karatsuba.txt), so the only way down is fewer multiplies per point.  With the base tables stored as
 // (y - x, y + x, 2 d x y) the unified mixed addition add-2008-hwcd-3 (a = -1) costs 7 multiplies against 8 M + 2 S for
 // XYZZ, and it is the SAME formula for P + Q, P + P, P + (-P) and P + 0: no infinity / doubling branches in the hot
 // loop.  d is a square here, so the law is not complete on the whole curve, but its exceptional pairs differ by a
