@@ -27,12 +27,19 @@ template <class C> __device__ __forceinline__ void block_tree_sum(xyzz_t &v, xyz
         if (threadIdx.x < o) { xyzz_t t; load_xyzz(t, sh + threadIdx.x); Grp<C>::add_ni(v, t); }
     }
 }
+template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh);
+// A bucket split into many pieces (skewed scalar sets: all-equal, tiny or sparse scalars put millions of points into
+// a handful of buckets) is summed by the whole warp -- lanes take pieces 32 apart, then a shared-memory tree -- instead
+// of serially by the one lane that owns the bucket.  Uniform scalars never enter this path (one piece per bucket).
+#define BIG_BUCKET_PIECES 2048   // below this the owning lanes walk their pieces in parallel; above, one lane would serialise the warp
 template <class C, bool INDIRECT>
 __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const uint32_t *__restrict__ piece_off, uint32_t m,
                                                        xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT,
                                                        uint32_t nchunks, size_t res_stride, size_t poff_stride) {
     __shared__ xyzz_t sh[64];
+    __shared__ xyzz_t shw[INDIRECT ? 4 : 1][INDIRECT ? 17 : 1];     // per warp: 16 tree slots + 1 hand-over slot
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the outputs exactly
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     xyzz_t run, tot, b;
     Grp<C>::set_inf(run);
     Grp<C>::set_inf(tot);
@@ -42,8 +49,24 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
         if (INDIRECT) {        // a bucket = the sum of its pieces, over every chunk the point set was accumulated in
             for (uint32_t ch = 0; ch < nchunks; ch++) {
                 const uint32_t *po = piece_off + ch * poff_stride;
-                uint32_t p0 = po[k], p1 = po[k + 1];
-                for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, in + ch * res_stride + q); Grp<C>::add_ni(run, b); }
+                const uint32_t p0 = po[k], p1 = po[k + 1];
+                const xyzz_t *src = in + ch * res_stride;
+                const bool big = (blockDim.x & 31) == 0 && p1 - p0 > BIG_BUCKET_PIECES;      // whole warps only
+                uint32_t todo = __ballot_sync(0xffffffffu, big);
+                while (todo) {                                      // warp-uniform: every lane walks the same list
+                    const int owner = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t q0 = __shfl_sync(0xffffffffu, p0, owner), q1 = __shfl_sync(0xffffffffu, p1, owner);
+                    xyzz_t part;
+                    Grp<C>::set_inf(part);
+                    for (uint32_t q = q0 + lane; q < q1; q += 32) { load_xyzz(b, src + q); Grp<C>::add_ni(part, b); }
+                    warp_sum<C>(part, shw[warp]);
+                    if (lane == 0) store_xyzz(&shw[warp][16], part);
+                    __syncwarp();
+                    if ((int)lane == owner) { load_xyzz(b, &shw[warp][16]); Grp<C>::add_ni(run, b); }
+                    __syncwarp();
+                }
+                if (!big) for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, src + q); Grp<C>::add_ni(run, b); }
             }
         } else {
             load_xyzz(b, in + k);
