@@ -1,5 +1,7 @@
 """GPU parity tests proper (-m gpu): every call goes through the C ABI of libb200msm.so and is compared with the
 CPU oracle bit-exactly after normalising to canonical affine (the MSM result is a unique group element)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -333,3 +335,24 @@ def test_c_harness(M):
     p = subprocess.run([build_c_harness(), "12"], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "msm_harness ok" in p.stdout
+
+
+def test_harness_fixture_directory(M, oracle, tmp_path):
+    """msm_correctness of the reference's CPU harness (test_naive_harness/tests/msm.rs:86-98): data from
+    TEST_LOAD_DATA_FROM (written here first, as TEST_WRITE_DATA_TO would), 4 batches, results vs arkworks_results.bin."""
+    import harness_data as HD
+    O = oracle
+    d = os.environ.get("TEST_LOAD_DATA_FROM")
+    if not d:
+        n, batches = 1 << 10, 4
+        pts = np.tile(O.gen_points(64, seed=93), (n // 64, 1))
+        sc = O.gen_scalars(n * batches, seed=94)
+        res = np.concatenate([O.jac_to_affine(O.ark_msm(pts, sc[b * n:(b + 1) * n])) for b in range(batches)])
+        d = str(tmp_path)
+        HD.write(O, d, pts, sc, res)
+    batches, pts, sc, want = HD.load(O, d)
+    ctx = M.multi_scalar_mult_init(pts)
+    got = M.multi_scalar_mult(ctx, pts, sc)
+    ctx.free()
+    for b in range(batches):
+        assert np.array_equal(O.jac_to_affine(got[b])[0], want[b]), b

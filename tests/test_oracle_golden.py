@@ -112,3 +112,16 @@ def test_pippenger_vs_naive_4096(oracle):
     b = oracle.jac_to_affine(oracle.naive_msm(aff, sc))
     assert a.tobytes() == b.tobytes()
     assert oracle.jac_eq(oracle.ark_msm(aff, sc), oracle.naive_msm(aff, sc))
+
+
+def test_harness_fixture_files_roundtrip(oracle, tmp_path):
+    """TEST_WRITE_DATA_TO / TEST_LOAD_DATA_FROM files of the reference's CPU harness (tests/harness_data.py)."""
+    import harness_data as HD
+    n, batches = 64, 2
+    pts = oracle.gen_points(n, seed=91)
+    sc = oracle.gen_scalars(n * batches, seed=92)
+    res = np.concatenate([oracle.jac_to_affine(oracle.ark_msm(pts, sc[b * n:(b + 1) * n])) for b in range(batches)])
+    HD.write(oracle, str(tmp_path), pts, sc, res)
+    assert os.path.getsize(tmp_path / "points.bin") == 8 + 48 * n and os.path.getsize(tmp_path / "scalars.bin") == 8 + 32 * n * batches
+    b2, pts2, sc2, res2 = HD.load(oracle, str(tmp_path))
+    assert b2 == batches and np.array_equal(pts2, pts) and np.array_equal(sc2, sc) and np.array_equal(res2, res)
