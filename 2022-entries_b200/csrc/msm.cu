@@ -158,7 +158,9 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     CK(dmalloc(&ctx->part_xyzz, 1));
     // two-level scatter when the list array is far beyond L2: bins of <= 24 MB of list each, at most BIN_MAX bins
     ctx->nbins = 0;
-    if (ctx->max_refs * 4 > (512ull << 20) && ctx->W <= 16 && !getenv("B200MSM_DIRECT_SCATTER")) {
+    uint64_t bin_min_bytes = 512ull << 20;
+    if (const char *e = getenv("B200MSM_BIN_MIN_MB")) bin_min_bytes = (uint64_t)atoll(e) << 20;      // tests: force the two-level path
+    if (ctx->max_refs * 4 > bin_min_bytes && ctx->W <= 16 && !getenv("B200MSM_DIRECT_SCATTER")) {
         uint64_t want = (ctx->max_refs * 4 + (24ull << 20) - 1) / (24ull << 20);       // bins needed
         int lg_nb = 0; while ((1ull << lg_nb) < nb) lg_nb++;
         int lg_bins = 0; while ((1ull << lg_bins) < want && lg_bins < 8) lg_bins++;
