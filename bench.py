@@ -181,7 +181,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL logs to stdout; the bench prints exactly one JSON line there
+        os.environ["NCCL_DEBUG"] = "NONE"      # NCCL logs (even its version banner) to stdout; the bench prints exactly one JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lg = args.log_n
     n = 1 << lg
