@@ -63,6 +63,7 @@ def lib():
     L.b200msm_msm_host.argtypes = [vp, vp, u64, u64, vp]
     L.b200msm_msm_partial_device.argtypes = [vp, vp, u64, vp]
     L.b200msm_combine_device.argtypes = [vp, vp, i32, vp]
+    L.b200msm_msm_partial_host.argtypes = [vp, vp, u64, vp]
     L.b200msm_sync.argtypes = [vp]
     L.b200msm_get_info.argtypes = [vp, ctypes.POINTER(u64)]
     L.b200msm_get_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
@@ -92,7 +93,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
-    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
+    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
     "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "b200msm_test_grp_op", "mult_pippenger_init", "mult_pippenger_inf",
     "mult_pippenger_free", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
 ]
@@ -265,6 +266,10 @@ class Engine:
 
     def msm_partial_device(self, scalars_dev_ptr, n, out_xyzz_dev_ptr):
         self._ck(lib().b200msm_msm_partial_device(self.h, ctypes.c_void_p(scalars_dev_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_partial_device")
+
+    def msm_partial_host(self, scalars_host_ptr, n, out_xyzz_dev_ptr):
+        """scalars_host_ptr: address of n * 32 bytes of (pinned) host memory, valid until sync()."""
+        self._ck(lib().b200msm_msm_partial_host(self.h, ctypes.c_void_p(scalars_host_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_partial_host")
 
     def combine_device(self, xyzz_dev_ptr, count, out_dev_ptr):
         self._ck(lib().b200msm_combine_device(self.h, ctypes.c_void_p(xyzz_dev_ptr), count, ctypes.c_void_p(out_dev_ptr)), "combine_device")

@@ -557,6 +557,37 @@ int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, vo
     return 0;
 }
 
+// Upload one batch of scalars from host memory and run it, the batch split into chunks of bases when it is large so that
+// chunk k+1 uploads while chunk k accumulates (each chunk into its own bucket sums, one shared reduction at the end).
+// Nothing else can hide the upload of the first batch of a call.  Stands in for the 1/4 + 3/4 split of the reference's
+// fastest entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).  buf: device staging of n x 32 bytes.
+static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_t n, uint8_t *buf, cudaEvent_t buf_free, void *out_jac, void *out_xyzz) {
+    int rc = 0;
+    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : 1);
+    if (nch > 8) nch = 8;
+    if ((uint64_t)nch > n) nch = 1;
+    if (nch > 1) { rc = ensure_chunks(ctx, nch); if (rc) return rc; }
+    CK(cudaStreamWaitEvent(ctx->copy_stream, buf_free, 0));
+    const uint64_t per = (n + nch - 1) / nch;
+    for (int ch = 0; ch < nch; ch++) {
+        const uint64_t first = (uint64_t)ch * per, cnt = first + per <= n ? per : n - first;
+        CK(cudaMemcpyAsync(buf + first * 32, scalars_host + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_chunk[ch], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[ch], 0));
+        rc = run_chunk(ctx, buf + first * 32, (uint32_t)first, (uint32_t)cnt, ch);
+        if (rc) return rc;
+    }
+    return run_reduce(ctx, nch, out_jac, out_xyzz);
+}
+
+int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_host || !out_xyzz_dev || ctx->n == 0 || n != ctx->n) return ctx->fail(-1, "b200msm_msm_partial_host: bad argument");
+    if (!ctx->scal_buf[0]) CK(cudaMalloc((void **)&ctx->scal_buf[0], (size_t)n * 32));
+    CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev);
+}
+
 int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uint64_t batches, void *out_jacobian_host) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!scalars_host || !out_jacobian_host || ctx->n == 0 || n != ctx->n || batches == 0) return ctx->fail(-1, "b200msm_msm_host: bad argument (bases not set or length mismatch)");
@@ -570,28 +601,11 @@ int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uin
     // the caller's stream may hold earlier work on these buffers
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
     CK(cudaEventRecord(ctx->ev_free[1], ctx->stream));
-    // The upload of batch b+1 overlaps the compute of batch b.  Nothing hides the upload of the FIRST batch, so that
-    // batch is split into chunks of bases: chunk k+1 uploads while chunk k accumulates (each chunk into its own
-    // bucket sums, one shared reduction at the end).  Stands in for the 1/4 + 3/4 split of the reference's fastest
-    // entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).
-    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : 1);
-    if (nch > 8) nch = 8;
-    if ((uint64_t)nch > n) nch = 1;
-    if (nch > 1) { rc = ensure_chunks(ctx, nch); if (rc) return rc; }
+    // The upload of batch b+1 overlaps the compute of batch b; the first batch is chunked (upload_and_run).
     for (uint64_t b = 0; b < batches; b++) {
         int k = (int)(b & 1);
-        if (b == 0 && nch > 1) {
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[k], 0));
-            const uint64_t per = (n + nch - 1) / nch;
-            for (int ch = 0; ch < nch; ch++) {
-                const uint64_t first = (uint64_t)ch * per, cnt = first + per <= n ? per : n - first;
-                CK(cudaMemcpyAsync(ctx->scal_buf[k] + first * 32, (const uint8_t *)scalars_host + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-                CK(cudaEventRecord(ctx->ev_chunk[ch], ctx->copy_stream));
-                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[ch], 0));
-                rc = run_chunk(ctx, ctx->scal_buf[k] + first * 32, (uint32_t)first, (uint32_t)cnt, ch);
-                if (rc) return rc;
-            }
-            rc = run_reduce(ctx, nch, ctx->out_dev, nullptr);
+        if (b == 0) {
+            rc = upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[k], ctx->ev_free[k], ctx->out_dev, nullptr);
             if (rc) return rc;
             CK(cudaEventRecord(ctx->ev_free[k], ctx->stream));
             continue;

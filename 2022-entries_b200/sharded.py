@@ -51,6 +51,10 @@ class CudaShardBackend:
     def partial(self, scalars_dev, out):
         self.e.msm_partial_device(scalars_dev.data_ptr(), self.n, out.data_ptr())
 
+    def partial_from_host(self, scalars_host, out):
+        """Pinned host scalars -> partial sum; the library chunks the upload against the accumulation."""
+        self.e.msm_partial_host(scalars_host.data_ptr(), self.n, out.data_ptr())
+
     def full(self, scalars_dev, out):
         self.e.msm_device(scalars_dev.data_ptr(), self.n, out.data_ptr())
 
@@ -70,14 +74,18 @@ class ShardedMsm:
         self.gathered = backend.new_buffer(backend.partial_bytes * self.world)
         self.out = backend.new_buffer(backend.out_bytes)
 
-    def msm_device(self, scalars_dev):
-        """scalars already on this rank's device.  Asynchronous on the backend's stream; returns the device buffer
-        holding the 144-byte Jacobian result (identical on every rank)."""
+    def msm_device(self, scalars_dev, host=False):
+        """scalars already on this rank's device (host=True: in pinned host memory, uploaded by the backend).
+        Asynchronous on the backend's stream; returns the device buffer holding the 144-byte Jacobian result
+        (identical on every rank)."""
         b = self.b
         if self.world == 1:
-            b.full(scalars_dev, self.out)
+            b.full(b.upload(scalars_dev) if host else scalars_dev, self.out)
             return self.out
-        b.partial(scalars_dev, self.partial)
+        if host and hasattr(b, "partial_from_host"):
+            b.partial_from_host(scalars_dev, self.partial)
+        else:
+            b.partial(b.upload(scalars_dev) if host else scalars_dev, self.partial)
         stream = getattr(b, "stream", None)
         if stream is not None:
             with torch.cuda.stream(stream):
@@ -89,8 +97,7 @@ class ShardedMsm:
 
     def msm(self, scalars_host):
         """End-to-end call: this rank's scalar slice in (pinned) host memory -> 144-byte result on the host."""
-        dev = self.b.upload(scalars_host)
-        out = self.msm_device(dev)
+        out = self.msm_device(scalars_host, host=True)
         stream = getattr(self.b, "stream", None)
         if stream is not None:
             with torch.cuda.stream(stream):

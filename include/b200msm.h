@@ -72,6 +72,10 @@ int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uin
 #define B200MSM_PARTIAL_BYTES 224
 int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev);
 int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev);
+/* The partial sum with this GPU's scalars in host memory (pinned for overlap): asynchronous like the device form; the
+ * upload is chunked against the accumulation exactly as in b200msm_msm_host.  scalars_host must stay valid until the
+ * stream reaches the end of the call (b200msm_sync). */
+int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev);
 
 int b200msm_sync(b200msm_ctx *ctx);
 
