@@ -1,3 +1,6 @@
+// SUPERSEDED by mul_bench.cu: the loop-invariant products below were partly strength-reduced by ptxas, so the
+// IMAD.WIDE figure this printed (63 / clk / SM) is twice the real rate (32; profiles/r01_mul_bench.txt).  Kept because
+// profiles/r01_imad_microbench.txt cites it.
 // Integer-pipe microbenchmark (measure, don't assume): issue rate of the instructions the Montgomery multiply is
 // made of, per SM per clock.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o imad_bench imad_bench.cu
 #include <cstdio>
