@@ -378,3 +378,22 @@ def test_partial_from_host_chunked(M, oracle, monkeypatch):
         e.sync()
         assert np.array_equal(O.jac_to_affine(out.cpu().numpy()), O.jac_to_affine(O.ark_msm(pts, sc)))
     e.close()
+
+
+def test_scalars_at_or_above_r(M, oracle):
+    """Scalars are 4 x u64 integers taken as-is.  Values in [r, 2^253) are legal inputs for arkworks (its windows cover
+    253 bits) and mean s mod r; the digit kernel reduces mod r first, so the results agree."""
+    O = oracle
+    r = O.constants(0)["r"]
+    n = 256
+    pts = O.gen_points(n, seed=111)
+    rng = np.random.default_rng(7)
+    vals = [int(r + int.from_bytes(rng.bytes(32), "little") % ((1 << 253) - r)) for _ in range(n)]
+    vals[0], vals[1], vals[2] = r, (1 << 253) - 1, r + 1
+    sc = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in vals), np.uint8).reshape(n, 32).copy()
+    ctx = M.multi_scalar_mult_init(pts)
+    out = M.multi_scalar_mult(ctx, pts, sc)
+    ctx.free()
+    assert np.array_equal(O.jac_to_affine(out[0]), O.jac_to_affine(O.ark_msm(pts, sc)))
+    reduced = np.frombuffer(b"".join((v % r).to_bytes(32, "little") for v in vals), np.uint8).reshape(n, 32)
+    assert np.array_equal(O.jac_to_affine(out[0]), O.jac_to_affine(O.naive_msm(pts, reduced)))
