@@ -563,7 +563,8 @@ int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, vo
 // fastest entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).  buf: device staging of n x 32 bytes.
 static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_t n, uint8_t *buf, cudaEvent_t buf_free, void *out_jac, void *out_xyzz) {
     int rc = 0;
-    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : 1);
+    // measured: 4 chunks at 2^26 (294.5 -> 272.1 ms) and 2^25, 2 chunks at 2^23 (8 GPUs: 51.4 -> 48.4 ms end to end)
+    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : (n >= (1ull << 22) ? 2 : 1));
     if (nch > 8) nch = 8;
     if ((uint64_t)nch > n) nch = 1;
     if (nch > 1) { rc = ensure_chunks(ctx, nch); if (rc) return rc; }
