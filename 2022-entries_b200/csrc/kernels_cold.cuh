@@ -28,10 +28,13 @@ template <class C> __device__ __forceinline__ void block_tree_sum(xyzz_t &v, xyz
     }
 }
 template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh);
-// A bucket split into many pieces (skewed scalar sets: all-equal, tiny or sparse scalars put millions of points into
-// a handful of buckets) is summed by the whole warp -- lanes take pieces 32 apart, then a shared-memory tree -- instead
-// of serially by the one lane that owns the bucket.  Uniform scalars never enter this path (one piece per bucket).
-#define BIG_BUCKET_PIECES 2048   // below this the owning lanes walk their pieces in parallel; above, one lane would serialise the warp
+// A bucket split into many pieces is summed by the whole warp -- lanes take pieces 32 apart, then a shared-memory tree --
+// instead of serially by the one lane that owns the bucket.  Two sources of such buckets: skewed scalar sets (all-equal,
+// tiny or sparse scalars put millions of points into a handful of buckets), and a top window of only a few bits (c not
+// dividing the scalar length: e.g. c = 21 leaves a 1-bit top window whose single bucket receives n/2 points).  Per warp
+// the cheaper of the two walks is chosen: serial costs max(pieces) adds, cooperative costs sum(pieces/32 + 6) over the
+// lanes with more than BIG_BUCKET_PIECES pieces.  Uniform scalars with a full top window never enter this path.
+#define BIG_BUCKET_PIECES 8
 template <class C, bool INDIRECT>
 __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const uint32_t *__restrict__ piece_off, uint32_t m,
                                                        xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT,
@@ -51,8 +54,18 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
                 const uint32_t *po = piece_off + ch * poff_stride;
                 const uint32_t p0 = po[k], p1 = po[k + 1];
                 const xyzz_t *src = in + ch * res_stride;
-                const bool big = (blockDim.x & 31) == 0 && p1 - p0 > BIG_BUCKET_PIECES;      // whole warps only
+                bool big = (blockDim.x & 31) == 0 && p1 - p0 > BIG_BUCKET_PIECES;            // whole warps only
                 uint32_t todo = __ballot_sync(0xffffffffu, big);
+                if (todo) {                                         // serial: max(pieces); cooperative: sum(pieces / 32 + 6)
+                    uint32_t serial = p1 - p0, coop = big ? (p1 - p0) / 32 + 6 : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const uint32_t t2 = __shfl_xor_sync(0xffffffffu, serial, o);
+                        serial = t2 > serial ? t2 : serial;
+                        coop += __shfl_xor_sync(0xffffffffu, coop, o);
+                    }
+                    if (coop >= serial) { todo = 0; big = false; }
+                }
                 while (todo) {                                      // warp-uniform: every lane walks the same list
                     const int owner = __ffs(todo) - 1;
                     todo &= todo - 1;
