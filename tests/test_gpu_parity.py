@@ -397,3 +397,32 @@ def test_scalars_at_or_above_r(M, oracle):
     assert np.array_equal(O.jac_to_affine(out[0]), O.jac_to_affine(O.ark_msm(pts, sc)))
     reduced = np.frombuffer(b"".join((v % r).to_bytes(32, "little") for v in vals), np.uint8).reshape(n, 32)
     assert np.array_equal(O.jac_to_affine(out[0]), O.jac_to_affine(O.naive_msm(pts, reduced)))
+
+
+def test_fp64_pipe_accumulator_flavour(M, oracle, monkeypatch):
+    """B200MSM_ACC=fp64: the accumulate kernel with its running sums on the FP64 pipe (te.cuh TeD, fpd.cuh) and the
+    tables in arkworks' Montgomery form -- same results as the default integer flavour, bit for bit."""
+    O = oracle
+    n = 1 << 12
+    pts = np.tile(O.gen_points(128, seed=121), (n // 128, 1))
+    pts[5] = 0
+    pts[5, 96] = 1
+    pts[9] = O.aff_neg(pts[8:9])[0]
+    sc = O.gen_scalars(n * 2, seed=122)
+    sc[9] = sc[8]
+    want = [O.jac_to_affine(O.ark_msm(pts, sc[b * n:(b + 1) * n]))[0] for b in range(2)]
+    outs = {}
+    for flavour in ("fp64", "int"):
+        monkeypatch.setenv("B200MSM_ACC", flavour)
+        ctx = M.multi_scalar_mult_init(pts)
+        outs[flavour] = M.multi_scalar_mult(ctx, pts, sc)
+        ctx.free()
+        for b in range(2):
+            assert np.array_equal(O.jac_to_affine(outs[flavour][b])[0], want[b]), (flavour, b)
+    assert np.array_equal(outs["fp64"], outs["int"])
+    # and the base-table read-back in that entry format
+    monkeypatch.setenv("B200MSM_ACC", "fp64")
+    e = M.Engine(0)
+    e.set_bases(pts)
+    assert np.array_equal(e.get_bases(0, 4), pts[:4, :96])
+    e.close()
