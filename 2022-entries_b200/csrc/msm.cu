@@ -224,13 +224,15 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
 // a11: base tables.  Per chunk of <= 2^22 points: table 0 entry = the point itself, table j = 2^(c*F) * table j-1,
 // doubled in XYZZ, normalised to short-Weierstrass affine (one inversion per 16 points), then converted to the curve's
 // table-entry form.  Only two affine chunk buffers and one XYZZ chunk buffer of scratch are alive.
-struct table_scratch_t { affine_t *sw[2] = {nullptr, nullptr}; xyzz_t *tmp = nullptr; uint32_t cap = 0; };
+struct table_scratch_t {           // freed on every exit path, error returns included
+    affine_t *sw[2] = {nullptr, nullptr}; xyzz_t *tmp = nullptr; uint8_t *raw = nullptr; uint32_t cap = 0;
+    ~table_scratch_t() { cudaFree(sw[0]); cudaFree(sw[1]); cudaFree(tmp); cudaFree(raw); }
+};
 static int scratch_alloc(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t cap) {
     sc.cap = cap;
     CK(dmalloc(&sc.sw[0], cap)); CK(dmalloc(&sc.sw[1], cap)); CK(dmalloc(&sc.tmp, cap));
     return 0;
 }
-static void scratch_free(table_scratch_t &sc) { cudaFree(sc.sw[0]); cudaFree(sc.sw[1]); cudaFree(sc.tmp); }
 // sc.sw[0] holds cnt affine points starting at index `first`: emit their entries into every table
 template <class C> static void emit_tables(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t first, uint32_t cnt) {
     const size_t eb = ctx->entry_bytes;
@@ -268,7 +270,6 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    scratch_free(sc);
     return 0;
 }
 
@@ -276,8 +277,8 @@ template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_h
     const uint64_t chunk = 1ull << 22;
     table_scratch_t sc;
     int rc = scratch_alloc(ctx, sc, (uint32_t)(n < chunk ? n : chunk)); if (rc) return rc;
-    uint8_t *raw = nullptr;
-    CK(cudaMalloc((void **)&raw, (size_t)((n < chunk ? n : chunk) * stride)));
+    CK(cudaMalloc((void **)&sc.raw, (size_t)((n < chunk ? n : chunk) * stride)));
+    uint8_t *raw = sc.raw;
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
     for (uint64_t first = 0; first < n; first += chunk) {
         uint64_t cnt = n - first < chunk ? n - first : chunk;
@@ -287,8 +288,6 @@ template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_h
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    cudaFree(raw);
-    scratch_free(sc);
     return 0;
 }
 
