@@ -58,7 +58,7 @@ template <class C> struct ScalarOps {
 
 // walks the signed digits of scalar i (the scalar of base number gi): fn(bucket key, point reference) for every
 // non-zero digit
-template <class C, class FN>
+template <class C, int MAXW = 0, class FN>
 __device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scalars, uint32_t i, uint32_t gi, uint32_t table_stride, int c, int W, int F, FN fn) {
     uint32_t s[9];
     {
@@ -67,12 +67,14 @@ __device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scal
         s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     }
     uint32_t(&s8)[8] = reinterpret_cast<uint32_t(&)[8]>(s);
-    ScalarOps<C>::mod_r(s8);
+    if (s[7] >= C::r(7)) ScalarOps<C>::mod_r(s8);      // top word below r's: already reduced (every harness scalar is)
     bool neg = ScalarOps<C>::fold_top_bit(s8);
     s[8] = 0;
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     uint32_t carry = 0;
-    for (int w = 0; w < W; w++) {
+#pragma unroll
+    for (int w = 0; w < (MAXW > 0 ? MAXW : W); w++) {       // MAXW > 0: compile-time trip count, so fn may index registers by w
+        if (MAXW > 0 && w >= W) break;
         int pos = w * c;
         int wi = pos >> 5, sh = pos & 31;
         uint64_t v = (uint64_t)s[wi] | ((uint64_t)s[wi + 1 > 8 ? 8 : wi + 1] << 32);
@@ -81,7 +83,8 @@ __device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scal
         if (flip) d = (1u << c) - d;
         carry = flip ? 1u : 0u;
         if (d == 0) continue;
-        fn((uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + gi) | ((neg != flip) ? 0x80000000u : 0u));
+        if constexpr (MAXW > 0) fn(w, (uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + gi) | ((neg != flip) ? 0x80000000u : 0u));
+        else fn((uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + gi) | ((neg != flip) ? 0x80000000u : 0u));
     }
 }
 
@@ -93,6 +96,10 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     if (i >= n) return;
     const uint32_t gi = first + i;
     if (infmask[gi >> 5] & (1u << (gi & 31))) return;     // base at infinity contributes nothing
+    if (PASS == 0 && W <= 16) {        // large problems: compile-time trip count
+        for_each_digit<C, 16>(scalars, i, gi, table_stride, c, W, F, [&](int, uint32_t key, uint32_t) { atomicAdd(&counters[key], 1u); });
+        return;
+    }
     for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
         if (PASS == 0) {
             atomicAdd(&counters[key], 1u);
@@ -127,7 +134,13 @@ __global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restri
     uint32_t i = blockIdx.x * BIN_TPB + threadIdx.x;
     const uint32_t gi = first + i;
     const bool live = i < n && !(infmask[gi >> 5] & (1u << (gi & 31)));
-    if (live) for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t) { atomicAdd(&cnt[key >> bin_shift], 1u); });
+    // the digits are computed once and kept in registers for both passes (W <= 16 on this path)
+    uint32_t key[16], ref[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) key[w] = 0xffffffffu;
+    if (live) for_each_digit<C, 16>(scalars, i, gi, table_stride, c, W, F, [&](int w, uint32_t k, uint32_t r) { key[w] = k; ref[w] = r; });
+#pragma unroll
+    for (int w = 0; w < 16; w++) if (key[w] != 0xffffffffu) atomicAdd(&cnt[key[w] >> bin_shift], 1u);
     __syncthreads();
     // exclusive scan of the per-bin counts (BIN_MAX == BIN_TPB: one bin per thread) and one global reservation per bin
     {
@@ -146,10 +159,11 @@ __global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restri
     }
     __syncthreads();
     const uint32_t total = scan[BIN_TPB - 1];
-    if (live) for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
-        const uint32_t b = key >> bin_shift;
-        sorted[start[b] + atomicAdd(&cnt[b], 1u)] = make_uint2(key, ref);
-    });
+#pragma unroll
+    for (int w = 0; w < 16; w++) if (key[w] != 0xffffffffu) {
+        const uint32_t b = key[w] >> bin_shift;
+        sorted[start[b] + atomicAdd(&cnt[b], 1u)] = make_uint2(key[w], ref[w]);
+    }
     __syncthreads();
     // consecutive threads write consecutive pairs of a bin's run: ~W*256/bins pairs (x 8 bytes) per run
     for (uint32_t k = threadIdx.x; k < total; k += BIN_TPB) {
