@@ -65,6 +65,10 @@ def lib():
     L.b200msm_combine_device.argtypes = [vp, vp, i32, vp]
     L.b200msm_msm_partial_host.argtypes = [vp, vp, u64, vp]
     L.b200msm_sync.argtypes = [vp]
+    L.b200msm_variable_base_msm.argtypes = [i32, i32, vp, u64, u64, vp, u64, vp]
+    L.b200msm_variable_base_release.argtypes = []
+    L.mult_pippenger.argtypes = [vp, vp, sz, vp]
+    L.mult_pippenger.restype = _RustError
     L.b200msm_get_info.argtypes = [vp, ctypes.POINTER(u64)]
     L.b200msm_get_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.b200msm_reset_stage_stats.argtypes = [vp]
@@ -95,7 +99,7 @@ EXPORTED_SYMBOLS = [
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
     "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
     "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "b200msm_test_grp_op", "mult_pippenger_init", "mult_pippenger_inf",
-    "mult_pippenger_free", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
+    "mult_pippenger_free", "b200msm_variable_base_msm", "b200msm_variable_base_release", "mult_pippenger", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
 ]
 
 
@@ -175,6 +179,57 @@ def multi_scalar_mult(context, points, scalars):
     out = np.zeros((batches, PROJECTIVE_BYTES), np.uint8)
     err = lib().mult_pippenger_inf(ctypes.byref(context.ffi), _ptr(out), _ptr(pts), npoints, batches, _ptr(sc), AFFINE_BYTES)
     _take_rust_error(err, "mult_pippenger_inf")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The one-call form: arkworks' own trait function and the prover-side callers of it
+class VariableBaseMSM:
+    """`ark_ec::msm::VariableBaseMSM` (ark-ec 0.3.0; restated in the reference at P1A/speakspeak/src/util.rs:51-174):
+    one static function, bases and scalars in, one projective point out, no context."""
+
+    @staticmethod
+    def multi_scalar_mul(bases, scalars, curve=BLS12_377, device=0, stride=AFFINE_BYTES):
+        """bases: G1Affine records (`stride` bytes each: 104 arkworks, 96 without the infinity flag); scalars: 32-byte
+        integers.  The first min(len(bases), len(scalars)) pairs are used, as arkworks does; empty input -> zero.
+        Returns uint8[144] (Jacobian x, y, z)."""
+        pts = _as_u8(bases, stride, "bases")
+        sc = _as_u8(scalars, SCALAR_BYTES, "scalars")
+        out = np.zeros(PROJECTIVE_BYTES, np.uint8)
+        rc = lib().b200msm_variable_base_msm(curve, device, _ptr(pts) if pts.size else None, pts.size // stride, stride,
+                                             _ptr(sc) if sc.size else None, sc.size // SCALAR_BYTES, _ptr(out))
+        if rc != 0:
+            raise MsmError(f"b200msm_variable_base_msm: {rc}: {lib().b200msm_last_error(None).decode()}")
+        return out
+
+    @staticmethod
+    def release():
+        """Free the device buffers the one-call form keeps between calls."""
+        lib().b200msm_variable_base_release()
+
+
+class VariableBase:
+    """snarkVM's dispatcher (team-division/prize2-posw-gpu/storswiftlabs/snarkVM/algorithms/src/msm/variable_base/
+    mod.rs:120-157): `VariableBase::msm(bases, scalars)`.  The reference tries the GPU and falls back to its CPU
+    `batched::msm` when the GPU call fails; this mirror has no CPU path, a failed GPU call raises."""
+
+    @staticmethod
+    def msm(bases, scalars):
+        return VariableBaseMSM.multi_scalar_mul(bases, scalars, BLS12_377, 0)
+
+
+def multi_scalar_mult_blst(points, scalars):
+    """upstream sppark `multi_scalar_mult(points: &[blst_p1_affine], scalars: &[blst_scalar]) -> blst_p1`
+    (.../Jackytan2018/extern/sppark/sppark/poc/blst-cuda/src/lib.rs:38-53) over `mult_pippenger`: 96-byte points."""
+    pts = _as_u8(points, 96, "points")
+    sc = _as_u8(scalars, SCALAR_BYTES, "scalars")
+    if pts.size // 96 != sc.size // SCALAR_BYTES:
+        raise MsmError("length mismatch")                            # the Rust shim panics with the same message
+    if pts.size == 0:
+        raise MsmError("empty input")                                # the Rust shim indexes points[0] and panics
+    out = np.zeros(PROJECTIVE_BYTES, np.uint8)
+    err = lib().mult_pippenger(_ptr(out), _ptr(pts), pts.size // 96, _ptr(sc))
+    _take_rust_error(err, "mult_pippenger")
     return out
 
 

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/b200msm.h"
@@ -40,6 +41,7 @@ struct b200msm_ctx {
 
     // plan
     uint64_t n = 0;
+    bool plan_ok = false;     // alloc_plan completed for n (a later set_bases of the same n reuses every buffer)
     int c = 0, W = 0, T = 0, F = 0;
     uint32_t nbuckets = 0, lmax = 0, max_pieces = 0;
     uint64_t max_refs = 0;
@@ -86,6 +88,7 @@ struct b200msm_ctx {
         scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
         red_steps.clear();
         n = 0;
+        plan_ok = false;
         chunks_alloc = 1;
     }
 };
@@ -127,6 +130,7 @@ static void choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
 template <class T> static cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
 
 static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
+    if (ctx->plan_ok && ctx->n == n) return 0;        // same size again (one-shot calls): plan and buffers stand
     ctx->free_plan();
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -159,9 +163,11 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     // two-level scatter when the list array is far beyond L2: bins of <= 24 MB of list each, at most BIN_MAX bins
     ctx->nbins = 0;
     uint64_t bin_min_bytes = 512ull << 20;
+    uint64_t bin_bytes = 24ull << 20;
     if (const char *e = getenv("B200MSM_BIN_MIN_MB")) bin_min_bytes = (uint64_t)atoll(e) << 20;      // tests: force the two-level path
+    if (const char *e = getenv("B200MSM_BIN_KB")) { bin_bytes = (uint64_t)atoll(e) << 10; if (bin_bytes == 0) bin_bytes = 1024; }   // ... with many bins at small n
     if (ctx->max_refs * 4 > bin_min_bytes && ctx->W <= 16 && !getenv("B200MSM_DIRECT_SCATTER")) {
-        uint64_t want = (ctx->max_refs * 4 + (24ull << 20) - 1) / (24ull << 20);       // bins needed
+        uint64_t want = (ctx->max_refs * 4 + bin_bytes - 1) / bin_bytes;               // bins needed
         int lg_nb = 0; while ((1ull << lg_nb) < nb) lg_nb++;
         int lg_bins = 0; while ((1ull << lg_bins) < want && lg_bins < 8) lg_bins++;
         if (lg_bins > lg_nb) lg_bins = lg_nb;
@@ -217,6 +223,7 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     uint32_t last_n = lv.back().n_out;
     fin.term[fin.nterms++] = {cur_arr, last_n, last_n, 0, 0};            // sum of all buckets
     fin.term[fin.nterms++] = {cur_arr, last_n, last_n, shift, 1};        // 2^shift * W0(S_last)
+    ctx->plan_ok = true;
     return 0;
 }
 
@@ -670,6 +677,56 @@ int b200msm_get_stage_ms_sum(b200msm_ctx *ctx, float stage_ms_sum[6], uint64_t *
     return 0;
 }
 
+// ---- one-call form: arkworks VariableBaseMSM::multi_scalar_mul(bases, scalars) ---------------------------------
+// The literal shape of ark-ec 0.3 multi_scalar_mul (P1A/speakspeak/src/util.rs:51-58: size = min(bases.len(), scalars.len()),
+// empty -> zero), of upstream sppark's one-shot mult_pippenger (team-division/prize2-posw-gpu/storswiftlabs/snarkVM/
+// algorithms/cuda/pippenger.cu:19-25, bound by .../Jackytan2018/extern/sppark/sppark/poc/blst-cuda/src/lib.rs:21-53) and of
+// snarkVM's VariableBase::msm -> cuda::msm_cuda dispatch (.../snarkVM/algorithms/src/msm/variable_base/mod.rs:120-157).
+// Bases change from call to call, so the plan is ONE table (no 2^(cj) P precompute: building T tables costs ~23 (T - 1)
+// doublings per point, far more than the MSM it would save) and the context of a (curve, device) pair is kept between
+// calls (as sppark keeps a static pippenger_t per device), so repeated calls of one size re-use every device buffer.
+static const uint64_t R_MOD_P[2][6] = {     // 2^384 mod p: the Montgomery one of the arkworks zero (1, 1, 0)
+    {0x02cdffffffffff68ull, 0x51409f837fffffb1ull, 0x9f7db3a98a7d3ff2ull, 0x7b4e97b76e7c6305ull, 0x4cf495bf803c84e8ull, 0x008d6661e2fdf49aull},
+    {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48985753c758baull, 0x77ce585370525745ull, 0x5c071a97a256ec6dull, 0x15f65ec3fa80e493ull}};
+static const int ONESHOT_MAX_DEV = 16;
+static std::mutex g_oneshot_mu;
+static b200msm_ctx *g_oneshot[2][ONESHOT_MAX_DEV] = {};
+
+int b200msm_variable_base_msm(int curve, int device, const void *affine_host, uint64_t nbases, uint64_t stride,
+                              const void *scalars_host, uint64_t nscalars, void *out_jacobian_host) {
+    if ((curve != 0 && curve != 1) || device < 0 || device >= ONESHOT_MAX_DEV || !out_jacobian_host || stride < 96 || (stride & 7)) {
+        g_create_error = "b200msm_variable_base_msm: bad argument";
+        return -1;
+    }
+    const uint64_t n = nbases < nscalars ? nbases : nscalars;
+    if (n > 0 && (!affine_host || !scalars_host)) { g_create_error = "b200msm_variable_base_msm: null input"; return -1; }
+    std::lock_guard<std::mutex> lock(g_oneshot_mu);
+    b200msm_ctx *&ctx = g_oneshot[curve][device];
+    if (!ctx) {                                       // also the no-device failure: the empty MSM has no CPU path either
+        int rc = b200msm_create(&ctx, curve, device, 0, 1);
+        if (rc) { ctx = nullptr; return rc; }
+    }
+    if (n == 0) {
+        uint64_t *o = (uint64_t *)out_jacobian_host;
+        for (int i = 0; i < 6; i++) { o[i] = R_MOD_P[curve][i]; o[6 + i] = R_MOD_P[curve][i]; o[12 + i] = 0; }
+        return 0;
+    }
+    int rc = b200msm_set_bases(ctx, affine_host, n, stride);
+    if (rc == 0) rc = b200msm_msm_host(ctx, scalars_host, n, 1, out_jacobian_host);
+    if (rc) {                                         // keep the message, drop the context: the next call starts clean
+        g_create_error = ctx->err;
+        b200msm_destroy(ctx);
+        ctx = nullptr;
+    }
+    return rc;
+}
+
+int b200msm_variable_base_release(void) {
+    std::lock_guard<std::mutex> lock(g_oneshot_mu);
+    for (auto &row : g_oneshot) for (b200msm_ctx *&c : row) if (c) { b200msm_destroy(c); c = nullptr; }
+    return 0;
+}
+
 // ---- element-wise test entry points ----------------------------------------------------------
 static int test_fail(const char *what, cudaError_t e) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -754,6 +811,13 @@ RustError mult_pippenger_free(MultiScalarMultContext *context) {
     if (!context || !context->context) return rust_error(-1, "mult_pippenger_free: context not initialised");
     b200msm_destroy((b200msm_ctx *)context->context);
     context->context = nullptr;
+    return rust_error(0, nullptr);
+}
+
+// upstream sppark's one-shot form: blst_p1_affine points (96 bytes: x, y, no infinity flag), BLS12-377 in the snarkVM build
+RustError mult_pippenger(void *out, const void *points, size_t npoints, const void *scalars) {
+    int rc = b200msm_variable_base_msm(B200MSM_BLS12_377, 0, points, npoints, 96, scalars, npoints, out);
+    if (rc) return rust_error(rc, b200msm_last_error(nullptr));
     return rust_error(0, nullptr);
 }
 

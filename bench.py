@@ -315,6 +315,29 @@ def main():
         except Exception as ex:          # pinned 8 GiB may not be available everywhere; the headline does not depend on it
             contest = {"skipped": str(ex)[:120]}
 
+    # ---- arkworks' own call shape (VariableBaseMSM::multi_scalar_mul: bases AND scalars from host memory, no context, no
+    # table precompute), reported beside the headline; N = 1 only, 2^24 points (1.5 GiB of bases) at most
+    one_call = None
+    if world == 1 and not args.no_e2e:
+        try:
+            m = min(n_local, 1 << 24)
+            hb = eng.get_bases(0, m)                                   # uint8[m, 96]: x, y in arkworks' Montgomery form
+            hs = host_scal.numpy()[:m * 32]
+            V = M.VariableBaseMSM
+            r1 = V.multi_scalar_mul(hb, hs, stride=96)                 # first call: allocates the one-table plan
+            t0 = time.perf_counter()
+            for _ in range(2):
+                r1 = V.multi_scalar_mul(hb, hs, stride=96)
+            dt = (time.perf_counter() - t0) / 2
+            exp1 = KA.expected_affine(O, 0, KA.dot_mod_r(hs.reshape(m, 32), logs[:m], r_mod))
+            ok = bool(np.array_equal(O.jac_to_affine(r1)[0], exp1))
+            V.release()
+            one_call = {"log_n": m.bit_length() - 1, "ms": dt * 1e3, "points_per_s": m / dt, "bit_exact": ok,
+                        "h2d_bytes": m * (96 + 32), "api": "VariableBaseMSM.multi_scalar_mul -> b200msm_variable_base_msm (pageable host bases + pinned scalars)"}
+            del hb
+        except Exception as ex:
+            one_call = {"skipped": str(ex)[:120]}
+
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -360,7 +383,7 @@ def main():
                          "note": "integer-pipe bound by construction; see int_pipe"},
             "int_pipe": {"imad_wide_per_launch": madds * imad_per_madd, "achieved_per_s": int_ach, "peak_per_s": int_peak, "frac": int_ach / int_peak,
                          "peak_source": "32 IMAD.WIDE lanes/clk/SM measured (profiles/r01_mul_bench.txt) x 148 SMs x sampled SM clock"},
-            "cpu_baseline": cpu, "e2e": e2e, "contest_call": contest, "gpu_launches": launches_per_msm * args.steps, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "contest_call": contest, "one_call": one_call, "gpu_launches": launches_per_msm * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -79,6 +79,18 @@ int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_
 
 int b200msm_sync(b200msm_ctx *ctx);
 
+/* arkworks' VariableBaseMSM::multi_scalar_mul(bases, scalars) in ONE call, no context: the first
+ * min(nbases, nscalars) pairs are used, an empty input gives the arkworks zero (ark-ec 0.3.0, restated in the reference
+ * at P1A/speakspeak/src/util.rs:51-58), everything in host memory, result = one 144-byte Jacobian point.  This is also the
+ * shape of snarkVM's VariableBase::msm -> cuda::msm_cuda dispatch (team-division/prize2-posw-gpu/storswiftlabs/snarkVM/
+ * algorithms/src/msm/variable_base/mod.rs:120-157).  Bases are uploaded on every call and used without table
+ * precomputation (one table); the library keeps one context per (curve, device) between calls so repeated calls of one
+ * size re-use their device buffers -- b200msm_variable_base_release() frees them.  Calls are serialised by a mutex.
+ * On failure b200msm_last_error(NULL) describes it.  No CPU path: -2 without a CUDA device, the empty input included. */
+int b200msm_variable_base_msm(int curve, int device, const void *affine_host, uint64_t nbases, uint64_t stride,
+                              const void *scalars_host, uint64_t nscalars, void *out_jacobian_host);
+int b200msm_variable_base_release(void);
+
 /* Plan and measurements of the last run.  info[0..7] = n, window bits c, windows W, tables T, folded windows F,
  * buckets, Lmax, kernel launches of the last MSM.  stage_ms[0..5] = digits+histogram, scan+scatter, pieces,
  * accumulate, bucket reduce, finalize (CUDA events on the context's stream; valid after b200msm_sync). */
@@ -112,6 +124,11 @@ RustError mult_pippenger_inf(MultiScalarMultContext *context, uint64_t *out, con
                              size_t npoints, size_t batch_size, const void *scalars, size_t ffi_affine_sz);
 /* not in the reference (its contexts leak): release a Family-A context */
 RustError mult_pippenger_free(MultiScalarMultContext *context);
+/* upstream sppark's one-shot call (team-division/prize2-posw-gpu/storswiftlabs/snarkVM/algorithms/cuda/pippenger.cu:19-25,
+ * bound by .../Jackytan2018/extern/sppark/sppark/poc/blst-cuda/src/lib.rs:21-53): npoints blst_p1_affine records of
+ * 96 bytes (x, y Montgomery, no infinity flag), npoints scalars, out = blst_p1 (144-byte Jacobian); BLS12-377, device 0.
+ * An adapter over b200msm_variable_base_msm. */
+RustError mult_pippenger(void *out, const void *points, size_t npoints, const void *scalars);
 
 /* ---- 2. Family B: yrrid / combined-top-solutions -------------------------------------------------------------- */
 void *MSMAllocContext(int32_t maxPoints, int32_t maxBatches);

@@ -47,6 +47,15 @@ def test_no_cpu_fallback(M):
         M.multi_scalar_mult_init(pts)
     with pytest.raises(M.MsmError):
         M.YrridContext()
+    sc = np.zeros((4, 32), np.uint8)
+    with pytest.raises(M.MsmError, match="no CPU path"):
+        M.VariableBaseMSM.multi_scalar_mul(pts, sc)
+    with pytest.raises(M.MsmError, match="no CPU path"):
+        M.VariableBaseMSM.multi_scalar_mul(pts[:0], sc[:0])          # not even the empty MSM is answered on the CPU
+    with pytest.raises(M.MsmError):
+        M.VariableBase.msm(pts, sc)
+    with pytest.raises(M.MsmError):
+        M.multi_scalar_mult_blst(pts[:, :96], sc)
 
 
 def test_bad_arguments(M):
@@ -58,6 +67,14 @@ def test_bad_arguments(M):
     assert L.MSMFreeContext(None) == -1
     assert L.MSMRun(None, None, None, 0) == -1
     assert L.MSMAllocContext(0, 1) is None
+    out = np.zeros(144, np.uint8)
+    assert L.b200msm_variable_base_msm(2, 0, None, 0, 104, None, 0, out.ctypes.data_as(ctypes.c_void_p)) == -1     # curve
+    assert L.b200msm_variable_base_msm(0, 0, None, 0, 100, None, 0, out.ctypes.data_as(ctypes.c_void_p)) == -1     # stride
+    assert L.b200msm_variable_base_msm(0, 0, None, 0, 104, None, 0, None) == -1                                    # out
+    assert L.b200msm_variable_base_msm(0, 0, None, 4, 104, None, 4, out.ctypes.data_as(ctypes.c_void_p)) == -1     # inputs
+    assert L.b200msm_variable_base_release() == 0
+    with pytest.raises(M.MsmError, match="length mismatch"):
+        M.multi_scalar_mult_blst(np.zeros((4, 96), np.uint8), np.zeros((5, 32), np.uint8))
     with pytest.raises(M.MsmError):
         M.multi_scalar_mult(M.MultiScalarMultContext(), np.zeros((4, 104), np.uint8), np.zeros((5, 32), np.uint8))   # length mismatch
 

@@ -426,3 +426,73 @@ def test_fp64_pipe_accumulator_flavour(M, oracle, monkeypatch):
     e.set_bases(pts)
     assert np.array_equal(e.get_bases(0, 4), pts[:4, :96])
     e.close()
+
+
+def test_one_call_variable_base_msm(M, oracle, golden_instances):
+    """arkworks' own call shape, VariableBaseMSM::multi_scalar_mul(bases, scalars), through b200msm_variable_base_msm:
+    golden instances, min(len) truncation, the empty MSM, sizes changing between calls on the cached context, the snarkVM
+    dispatcher name and upstream sppark's 96-byte mult_pippenger."""
+    O = oracle
+    V = M.VariableBaseMSM
+    for k in (2, 3, 0):                                               # N = 256, 16, 16384: re-plans between calls
+        g = golden_instances[k]
+        out = V.multi_scalar_mul(g["aff"], g["scalars"])
+        assert O.compress(O.jac_to_affine(out)).tobytes() == g["result"], k
+    n = 3000
+    pts, sc = O.gen_points(n, seed=90), O.gen_scalars(n, seed=91)
+    pts[5] = 0
+    pts[5, 96] = 1                                                    # a base at infinity
+    exp = O.jac_to_affine(O.ark_msm(pts, sc))
+    a = V.multi_scalar_mul(pts, sc)
+    b = V.multi_scalar_mul(pts, sc)                                   # same size again: buffers re-used
+    assert np.array_equal(a, b) and np.array_equal(O.jac_to_affine(a), exp)
+    assert np.array_equal(O.jac_to_affine(M.VariableBase.msm(pts, sc)), exp)
+    # arkworks: size = min(bases.len(), scalars.len())
+    m = 1777
+    exp_m = O.jac_to_affine(O.ark_msm(pts[:m], sc[:m]))
+    assert np.array_equal(O.jac_to_affine(V.multi_scalar_mul(pts, sc[:m])), exp_m)
+    assert np.array_equal(O.jac_to_affine(V.multi_scalar_mul(pts[:m], sc)), exp_m)
+    # empty input -> the arkworks zero (1, 1, 0)
+    z = V.multi_scalar_mul(pts[:0], sc[:0])
+    one = np.frombuffer(O.constants(0)["R"].to_bytes(48, "little"), np.uint8)
+    assert np.array_equal(z[:48], one) and np.array_equal(z[48:96], one) and not z[96:].any()
+    # upstream sppark one-shot: 96-byte blst_p1_affine records (no infinity flag)
+    q = O.gen_points(512, seed=92)
+    s2 = O.gen_scalars(512, seed=93)
+    got = M.multi_scalar_mult_blst(np.ascontiguousarray(q[:, :96]), s2)
+    assert np.array_equal(O.jac_to_affine(got), O.jac_to_affine(O.ark_msm(q, s2)))
+    # second curve through the same entry point
+    p381, s381 = O.gen_points(700, seed=94, curve=1), O.gen_scalars(700, seed=95, curve=1)
+    got = V.multi_scalar_mul(p381, s381, curve=M.BLS12_381)
+    assert np.array_equal(O.jac_to_affine(got, 1), O.jac_to_affine(O.ark_msm(p381, s381, 1), 1))
+    V.release()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("cfg", [(16, 0), (16, 1), (20, 3)])
+def test_two_level_scatter_forced_at_small_size(M, oracle, monkeypatch, curve, cfg):
+    """The two-level scatter (k_digits_bin + k_bin_scatter) is chosen by size (lists > 512 MB, i.e. n >= 2^24); here it is
+    forced at 2^12 points with 1-KB bins (160-256 bins) so that it meets folded windows (tables 1 and 3: F = 16 and 5, a
+    bucket count that is not a power of two), both curves, skewed scalars and the oracle.  Two more launches than the
+    direct scatter prove the path ran."""
+    O = oracle
+    n = 1 << 12
+    pts = np.tile(O.gen_points(128, seed=71 + curve, curve=curve), (n // 128, 1))
+    pts[3] = 0
+    pts[3, 96] = 1
+    sc = O.gen_scalars(n, seed=72, curve=curve)
+    sc[100:1100] = sc[100]                                            # one heavy bucket per window
+    sc[2000:2100] = 0
+    want = O.jac_to_affine(O.ark_msm(pts, sc, curve), curve)[0]
+    launches = {}
+    for two_level in (False, True):
+        if two_level:
+            monkeypatch.setenv("B200MSM_BIN_MIN_MB", "0")
+            monkeypatch.setenv("B200MSM_BIN_KB", "1")
+        eng = M.Engine(curve, window_bits=cfg[0], tables=cfg[1])
+        eng.set_bases(pts)
+        got = _engine_result(M, O, eng, sc, curve)
+        launches[two_level] = eng.info()["launches"]
+        eng.close()
+        assert np.array_equal(got, want), (cfg, two_level)
+    assert launches[True] == launches[False] + 2
