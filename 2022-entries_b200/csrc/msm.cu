@@ -13,6 +13,7 @@
 #include "../../include/b200msm.h"
 #include "kernels_common.cuh"
 #include "launch.h"
+#include "copy_pool.h"
 
 using namespace b200msm;
 
@@ -23,6 +24,7 @@ static thread_local std::string g_create_error;
         cudaError_t e__ = (call);                                                                       \
         if (e__ != cudaSuccess) return ctx->fail((int)e__, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+
 
 struct red_step_t {
     int kind;                 // 0: reduce_slices through the piece table, 1: reduce_slices, 2: block_sum
@@ -64,6 +66,17 @@ struct b200msm_ctx {
     uint32_t nbins = 0;
     xyzz_t *res = nullptr, *red_buf = nullptr, *part_xyzz = nullptr;
     uint8_t *scal_buf[2] = {nullptr, nullptr};
+    uint8_t *raw_buf[2] = {nullptr, nullptr};   // one-call form: arkworks records of one upload step, double-buffered
+    affine_t *sw_buf = nullptr;                 //                the same step in the device representation
+    size_t raw_cap = 0;
+    cudaEvent_t ev_raw_copied[2] = {}, ev_raw_free[2] = {};
+    static const size_t SLOT_BYTES = 32u << 20;
+    uint8_t *slot[2] = {nullptr, nullptr};      // pinned staging for pageable sources (h2d)
+    cudaEvent_t slot_ev[2] = {};
+    bool slot_busy[2] = {false, false};
+    uint64_t slot_k = 0;
+    copy_pool_t *pool = nullptr;
+    int plan_chunks = 1;      // chunks the cost model charges the bucket reduction for (one-call form)
     uint8_t *out_dev = nullptr;      // batches x 144
     uint64_t out_dev_cap = 0;
     std::vector<red_step_t> red_steps;
@@ -82,10 +95,11 @@ struct b200msm_ctx {
     }
     void free_plan() {
         void *ptrs[] = {tables, infmask, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
-                        scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1], bin_cursor, staging};
+                        scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1], bin_cursor, staging, raw_buf[0], raw_buf[1], sw_buf};
         for (void *p : ptrs) if (p) cudaFree(p);
         tables = nullptr; infmask = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
         scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
+        raw_buf[0] = raw_buf[1] = nullptr; sw_buf = nullptr; raw_cap = 0;
         red_steps.clear();
         n = 0;
         plan_ok = false;
@@ -115,7 +129,7 @@ static void choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
         int F = (W + T - 1) / T;
         double buckets = (double)F * (double)(1ull << (c - 1));
         if (buckets > (double)(1u << 27)) continue;
-        double red = 28.0 * buckets;
+        double red = (28.0 + 14.0 * (ctx->plan_chunks - 1)) * buckets;      // + one full add per bucket per extra chunk
         double cost = 10.0 * (double)W * (double)n + red;
         if (cost < best) { best = cost; best_c = c; }
     }
@@ -227,6 +241,41 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     return 0;
 }
 
+// dst (device) <- src (caller's host memory) on stream st.  Pinned sources and small copies go straight to cudaMemcpyAsync;
+// pageable sources are staged through the context's pinned slots by the copy pool.  Returns once src has been read.
+static int h2d(b200msm_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    size_t min_bytes = 4u << 20;
+    if (const char *e = getenv("B200MSM_STAGE_MIN_KB")) min_bytes = (size_t)atoll(e) << 10;        // tests: stage small copies too
+    bool direct = bytes < min_bytes || getenv("B200MSM_NO_STAGING");
+    if (!direct) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, src) != cudaSuccess) cudaGetLastError();      // unknown to the runtime: pageable
+        else direct = a.type != cudaMemoryTypeUnregistered;
+    }
+    if (direct) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0; }
+    if (!ctx->pool) {
+        for (int i = 0; i < 2; i++) {
+            CK(cudaHostAlloc((void **)&ctx->slot[i], b200msm_ctx::SLOT_BYTES, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&ctx->slot_ev[i], cudaEventDisableTiming));
+        }
+        int p = (int)std::thread::hardware_concurrency() / 2;
+        if (const char *e = getenv("B200MSM_COPY_THREADS")) p = atoi(e);
+        p = p < 1 ? 1 : (p > 16 ? 16 : p);
+        ctx->pool = new copy_pool_t();
+        ctx->pool->start(p);
+    }
+    for (size_t off = 0; off < bytes; off += b200msm_ctx::SLOT_BYTES, ctx->slot_k++) {
+        const size_t len = bytes - off < b200msm_ctx::SLOT_BYTES ? bytes - off : b200msm_ctx::SLOT_BYTES;
+        const int b = (int)(ctx->slot_k & 1);
+        if (ctx->slot_busy[b]) CK(cudaEventSynchronize(ctx->slot_ev[b]));
+        ctx->pool->run(ctx->slot[b], (const uint8_t *)src + off, len);
+        CK(cudaMemcpyAsync((uint8_t *)dst + off, ctx->slot[b], len, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->slot_ev[b], st));
+        ctx->slot_busy[b] = true;
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // a11: base tables.  Per chunk of <= 2^22 points: table 0 entry = the point itself, table j = 2^(c*F) * table j-1,
 // doubled in XYZZ, normalised to short-Weierstrass affine (one inversion per 16 points), then converted to the curve's
@@ -289,7 +338,7 @@ template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_h
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
     for (uint64_t first = 0; first < n; first += chunk) {
         uint64_t cnt = n - first < chunk ? n - first : chunk;
-        CK(cudaMemcpyAsync(raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), cudaMemcpyHostToDevice, ctx->stream));
+        rc = h2d(ctx, raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), ctx->stream); if (rc) return rc;
         LaunchCold<C>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, sc.sw[0], ctx->infmask + first / 32);
         emit_tables<C>(ctx, sc, (uint32_t)first, (uint32_t)cnt);
         CK(cudaGetLastError());
@@ -462,6 +511,7 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     for (int r = 0; r < b200msm_ctx::EV_RING; r++) for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->evr[r][i]);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming); }
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_raw_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_raw_free[i], cudaEventDisableTiming); }
     if (e != cudaSuccess) {
         g_create_error = std::string("b200msm_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -480,6 +530,9 @@ int b200msm_destroy(b200msm_ctx *ctx) {
     for (auto &row : ctx->evr) for (auto &e : row) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]); }
+    for (int i = 0; i < 2; i++) { if (ctx->ev_raw_copied[i]) cudaEventDestroy(ctx->ev_raw_copied[i]); if (ctx->ev_raw_free[i]) cudaEventDestroy(ctx->ev_raw_free[i]); }
+    delete ctx->pool;
+    for (int i = 0; i < 2; i++) { if (ctx->slot[i]) cudaFreeHost(ctx->slot[i]); if (ctx->slot_ev[i]) cudaEventDestroy(ctx->slot_ev[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -583,7 +636,7 @@ static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_
         const uint64_t first = n * ((1ull << ch) - 1) / denom, end = ch + 1 == nch ? n : n * ((1ull << (ch + 1)) - 1) / denom;
         const uint64_t cnt = end - first;
         if (cnt == 0) continue;                  // tiny n: fewer, non-empty chunks
-        CK(cudaMemcpyAsync(buf + first * 32, scalars_host + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+        rc = h2d(ctx, buf + first * 32, scalars_host + first * 32, (size_t)cnt * 32, ctx->copy_stream); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_chunk[used], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[used], 0));
         rc = run_chunk(ctx, buf + first * 32, (uint32_t)first, (uint32_t)cnt, used);
@@ -624,7 +677,7 @@ int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uin
             continue;
         }
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[k], 0));
-        CK(cudaMemcpyAsync(ctx->scal_buf[k], (const uint8_t *)scalars_host + b * bytes, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        rc = h2d(ctx, ctx->scal_buf[k], (const uint8_t *)scalars_host + b * bytes, bytes, ctx->copy_stream); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));
         rc = run_msm(ctx, ctx->scal_buf[k], ctx->out_dev + b * 144, nullptr);
@@ -692,6 +745,72 @@ static const int ONESHOT_MAX_DEV = 16;
 static std::mutex g_oneshot_mu;
 static b200msm_ctx *g_oneshot[2][ONESHOT_MAX_DEV] = {};
 
+}  // extern "C"
+
+// Bases and scalars of one call stream through the device in steps: while step k's records are converted (arkworks ->
+// 28-bit limbs -> table entry: one shared inversion per GRP_BATCH points on BLS12-377) and while the chunk before
+// accumulates, the copy stream already uploads step k + 1.  The accumulate chunks are the ones of upload_and_run (own
+// bucket sums per chunk, one reduction over all of them), equal-sized here because the call is upload-bound, not
+// compute-bound: the exposed tail is one chunk's accumulation, not one chunk's upload.
+static int one_call_chunks(const b200msm_ctx *ctx, uint64_t n) {
+    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 23) ? 4 : (n >= (1ull << 21) ? 2 : 1));
+    if (nch > 8) nch = 8;
+    if ((uint64_t)nch * 32 > n) nch = 1;
+    return nch;
+}
+template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases, uint64_t n, uint64_t stride, const uint8_t *scalars, void *out_host) {
+    if (ctx->T != 1) return ctx->fail(-1, "one-call form needs a one-table plan");
+    const uint64_t step = 1ull << 21;                          // 2 M records (208 MB) per upload
+    const uint64_t cap = n < step ? n : step;
+    if (ctx->raw_cap < cap * stride) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < 2; i++) { cudaFree(ctx->raw_buf[i]); ctx->raw_buf[i] = nullptr; }
+        ctx->raw_cap = 0;
+        for (int i = 0; i < 2; i++) CK(cudaMalloc((void **)&ctx->raw_buf[i], (size_t)(cap * stride)));
+        ctx->raw_cap = (size_t)(cap * stride);
+    }
+    if (!ctx->sw_buf) CK(dmalloc(&ctx->sw_buf, (size_t)cap));
+    if (!ctx->scal_buf[0]) CK(cudaMalloc((void **)&ctx->scal_buf[0], (size_t)n * 32));
+    if (ctx->out_dev_cap < 1) { CK(cudaMalloc((void **)&ctx->out_dev, 144)); ctx->out_dev_cap = 1; }
+    const int nch = one_call_chunks(ctx, n);
+    int rc = 0;
+    if (nch > 1) { rc = ensure_chunks(ctx, nch); if (rc) return rc; }
+    CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));         // earlier work on this stream may still read the buffers
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+    uint64_t k = 0;
+    int used = 0;
+    for (int ch = 0; ch < nch; ch++) {
+        // chunk boundaries on multiples of 32: the conversion writes whole words of the infinity mask
+        const uint64_t first = (n * ch / nch) & ~31ull, end = ch + 1 == nch ? n : (n * (ch + 1) / nch) & ~31ull;
+        if (end <= first) continue;
+        for (uint64_t s = first; s < end; s += step, k++) {
+            const uint64_t cnt = end - s < step ? end - s : step;
+            const int b = (int)(k & 1);
+            if (k >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_raw_free[b], 0));
+            rc = h2d(ctx, ctx->raw_buf[b], bases + s * stride, (size_t)(cnt * stride), ctx->copy_stream); if (rc) return rc;
+            CK(cudaEventRecord(ctx->ev_raw_copied[b], ctx->copy_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_raw_copied[b], 0));
+            LaunchCold<C>::convert_points(ctx->stream, ctx->raw_buf[b], (uint32_t)cnt, (uint32_t)stride, ctx->sw_buf, ctx->infmask + s / 32);
+            LaunchCold<C>::make_entries(ctx->stream, ctx->sw_buf, (uint32_t)cnt, ctx->tables + s * ctx->entry_bytes, ctx->acc_mix == 0);
+            CK(cudaEventRecord(ctx->ev_raw_free[b], ctx->stream));
+        }
+        rc = h2d(ctx, ctx->scal_buf[0] + first * 32, scalars + first * 32, (size_t)(end - first) * 32, ctx->copy_stream); if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_chunk[used], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[used], 0));
+        rc = run_chunk(ctx, ctx->scal_buf[0] + first * 32, (uint32_t)first, (uint32_t)(end - first), used);
+        if (rc) return rc;
+        used++;
+    }
+    rc = run_reduce(ctx, used, ctx->out_dev, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, ctx->out_dev, 144, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" {
+
 int b200msm_variable_base_msm(int curve, int device, const void *affine_host, uint64_t nbases, uint64_t stride,
                               const void *scalars_host, uint64_t nscalars, void *out_jacobian_host) {
     if ((curve != 0 && curve != 1) || device < 0 || device >= ONESHOT_MAX_DEV || !out_jacobian_host || stride < 96 || (stride & 7)) {
@@ -699,7 +818,7 @@ int b200msm_variable_base_msm(int curve, int device, const void *affine_host, ui
         return -1;
     }
     const uint64_t n = nbases < nscalars ? nbases : nscalars;
-    if (n > 0 && (!affine_host || !scalars_host)) { g_create_error = "b200msm_variable_base_msm: null input"; return -1; }
+    if (n >= (1ull << 31) || (n > 0 && (!affine_host || !scalars_host))) { g_create_error = "b200msm_variable_base_msm: bad input"; return -1; }
     std::lock_guard<std::mutex> lock(g_oneshot_mu);
     b200msm_ctx *&ctx = g_oneshot[curve][device];
     if (!ctx) {                                       // also the no-device failure: the empty MSM has no CPU path either
@@ -711,8 +830,11 @@ int b200msm_variable_base_msm(int curve, int device, const void *affine_host, ui
         for (int i = 0; i < 6; i++) { o[i] = R_MOD_P[curve][i]; o[6 + i] = R_MOD_P[curve][i]; o[12 + i] = 0; }
         return 0;
     }
-    int rc = b200msm_set_bases(ctx, affine_host, n, stride);
-    if (rc == 0) rc = b200msm_msm_host(ctx, scalars_host, n, 1, out_jacobian_host);
+    int rc = check_ctx(ctx);
+    ctx->plan_chunks = one_call_chunks(ctx, n);       // the window plan knows the reduction sums over this many chunks
+    if (rc == 0) rc = alloc_plan(ctx, n);
+    if (rc == 0) rc = curve == 0 ? one_call_t<Bls12_377>(ctx, (const uint8_t *)affine_host, n, stride, (const uint8_t *)scalars_host, out_jacobian_host)
+                                 : one_call_t<Bls12_381>(ctx, (const uint8_t *)affine_host, n, stride, (const uint8_t *)scalars_host, out_jacobian_host);
     if (rc) {                                         // keep the message, drop the context: the next call starts clean
         g_create_error = ctx->err;
         b200msm_destroy(ctx);

@@ -496,3 +496,36 @@ def test_two_level_scatter_forced_at_small_size(M, oracle, monkeypatch, curve, c
         eng.close()
         assert np.array_equal(got, want), (cfg, two_level)
     assert launches[True] == launches[False] + 2
+
+
+def test_staged_upload_of_pageable_arrays(M, oracle, monkeypatch):
+    """Pageable host arrays (what the Rust harness passes) go through the pinned staging slots and the copy pool: forced
+    for small copies on every entry point that takes host arrays, then at 2^20 points through the one-call form (100 MB of
+    bases: the two 32-MB slots are re-used), against the closed form."""
+    import known_answer as KA
+    O = oracle
+    monkeypatch.setenv("B200MSM_STAGE_MIN_KB", "0")
+    monkeypatch.setenv("B200MSM_COPY_THREADS", "3")
+    n, batches = 1 << 11, 3
+    pts = np.tile(O.gen_points(64, seed=81), (n // 64, 1))
+    sc = O.gen_scalars(n * batches, seed=82)
+    exp = [O.jac_to_affine(O.ark_msm(pts, sc[b * n:(b + 1) * n])) for b in range(batches)]
+    ctx = M.multi_scalar_mult_init(pts)
+    out = M.multi_scalar_mult(ctx, pts, sc)
+    ctx.free()
+    for b in range(batches):
+        assert np.array_equal(O.jac_to_affine(out[b]), exp[b]), b
+    assert np.array_equal(O.jac_to_affine(M.VariableBaseMSM.multi_scalar_mul(pts, sc[:n])), exp[0])
+    M.VariableBaseMSM.release()
+    monkeypatch.delenv("B200MSM_STAGE_MIN_KB")
+    monkeypatch.delenv("B200MSM_COPY_THREADS")
+    n = 1 << 20
+    eng = M.Engine(0, tables=1)
+    eng.set_bases_generated(n, seed=77, mode=1, distinct=1)
+    hb = eng.get_bases(0, n)
+    eng.close()
+    sc = O.gen_scalars(n, seed=83)
+    t = KA.dot_mod_r(sc, KA.base_logs(n, 77, 1, 1), O.constants(0)["r"])
+    got = M.VariableBaseMSM.multi_scalar_mul(hb, sc, stride=96)
+    assert np.array_equal(O.jac_to_affine(got)[0], KA.expected_affine(O, 0, t))
+    M.VariableBaseMSM.release()

@@ -283,3 +283,12 @@ def test_fp64_te_accumulator(emuld, oracle):
         assert np.array_equal(out[:, 96], want[:, 96]), (op, reps)
         fin = want[:, 96] == 0
         assert np.array_equal(out[fin, :96], want[fin, :96]), (op, reps)
+
+
+def test_copy_pool_parallel_range_copy():
+    """csrc/copy_pool.h (the host threads behind the staged upload of pageable arrays): odd sizes and offsets, 1-16 threads."""
+    exe = os.path.join(HERE, "pool_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", os.path.join(HERE, "pool_test.cpp"), "-o", exe])
+    for threads in (1, 3, 8, 16):
+        p = subprocess.run([exe, str(threads)], capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0 and p.stdout.strip() == "ok", (threads, p.stdout, p.stderr)
