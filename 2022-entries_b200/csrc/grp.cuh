@@ -8,7 +8,7 @@
 
 namespace b200msm {
 
-#define GRP_BATCH 16      // points per thread in the entry conversion (one inversion per batch)
+#define GRP_BATCH 64      // points per thread in the entry conversion (one inversion per batch)
 
 template <class C> struct GrpXyzz {
     typedef Fp<C> F;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -76,6 +77,7 @@ struct b200msm_ctx {
     bool slot_busy[2] = {false, false};
     uint64_t slot_k = 0;
     copy_pool_t *pool = nullptr;
+    double h2d_ms = 0, h2d_wait_ms = 0;   // host time spent in h2d / of it waiting for a free slot (B200MSM_TRACE)
     int plan_chunks = 1;      // chunks the cost model charges the bucket reduction for (one-call form)
     uint8_t *out_dev = nullptr;      // batches x 144
     uint64_t out_dev_cap = 0;
@@ -264,15 +266,18 @@ static int h2d(b200msm_ctx *ctx, void *dst, const void *src, size_t bytes, cudaS
         ctx->pool = new copy_pool_t();
         ctx->pool->start(p);
     }
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     for (size_t off = 0; off < bytes; off += b200msm_ctx::SLOT_BYTES, ctx->slot_k++) {
         const size_t len = bytes - off < b200msm_ctx::SLOT_BYTES ? bytes - off : b200msm_ctx::SLOT_BYTES;
         const int b = (int)(ctx->slot_k & 1);
-        if (ctx->slot_busy[b]) CK(cudaEventSynchronize(ctx->slot_ev[b]));
+        if (ctx->slot_busy[b]) { const auto tw = std::chrono::steady_clock::now(); CK(cudaEventSynchronize(ctx->slot_ev[b])); ctx->h2d_wait_ms += ms_since(tw); }
         ctx->pool->run(ctx->slot[b], (const uint8_t *)src + off, len);
         CK(cudaMemcpyAsync((uint8_t *)dst + off, ctx->slot[b], len, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(ctx->slot_ev[b], st));
         ctx->slot_busy[b] = true;
     }
+    ctx->h2d_ms += ms_since(t0);
     return 0;
 }
 
@@ -760,7 +765,9 @@ static int one_call_chunks(const b200msm_ctx *ctx, uint64_t n) {
 }
 template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases, uint64_t n, uint64_t stride, const uint8_t *scalars, void *out_host) {
     if (ctx->T != 1) return ctx->fail(-1, "one-call form needs a one-table plan");
-    const uint64_t step = 1ull << 21;                          // 2 M records (208 MB) per upload
+    const uint64_t step = 1ull << 22;                          // 4 M records (416 MB) per upload: 65536 converting threads
+    const auto t_call = std::chrono::steady_clock::now();
+    ctx->h2d_ms = ctx->h2d_wait_ms = 0;
     const uint64_t cap = n < step ? n : step;
     if (ctx->raw_cap < cap * stride) {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -805,7 +812,16 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
     rc = run_reduce(ctx, used, ctx->out_dev, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_host, ctx->out_dev, 144, cudaMemcpyDeviceToHost, ctx->stream));
+    const double issue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     CK(cudaStreamSynchronize(ctx->stream));
+    if (getenv("B200MSM_TRACE")) {
+        float st[6] = {};
+        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&st[i], ctx->ev[i], ctx->ev[i + 1]);      // last chunk's stages + the reduction
+        fprintf(stderr, "b200msm one-call n=%llu c=%d W=%d F=%d chunks=%d: total %.1f ms, issued after %.1f ms, in h2d %.1f ms (waiting for a slot %.1f ms); "
+                "last chunk: digits %.1f scatter %.1f pieces %.1f accumulate %.1f, reduce %.1f finalize %.1f ms\n", (unsigned long long)n, ctx->c, ctx->W, ctx->F, nch,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), issue_ms, ctx->h2d_ms, ctx->h2d_wait_ms,
+                st[0], st[1], st[2], st[3], st[4], st[5]);
+    }
     return 0;
 }
 
