@@ -37,7 +37,8 @@ struct red_step_t {
 struct b200msm_ctx {
     int curve = 0, device = 0;
     int req_c = 0, req_tables = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, conv_stream = nullptr;   // conv: entry conversion of the one-call form (high priority)
+    cudaEvent_t ev_conv = nullptr;
     bool own_stream = true;
     std::string err;
     int sticky = 0;
@@ -513,6 +514,8 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); e = cudaStreamCreateWithPriority(&ctx->conv_stream, cudaStreamNonBlocking, hi); }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_conv, cudaEventDisableTiming);
     for (int r = 0; r < b200msm_ctx::EV_RING; r++) for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->evr[r][i]);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming); }
@@ -540,6 +543,8 @@ int b200msm_destroy(b200msm_ctx *ctx) {
     for (int i = 0; i < 2; i++) { if (ctx->slot[i]) cudaFreeHost(ctx->slot[i]); if (ctx->slot_ev[i]) cudaEventDestroy(ctx->slot_ev[i]); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->conv_stream) cudaStreamDestroy(ctx->conv_stream);
+    if (ctx->ev_conv) cudaEventDestroy(ctx->ev_conv);
     delete ctx;
     return 0;
 }
@@ -785,6 +790,12 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));         // earlier work on this stream may still read the buffers
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[0], 0));
+    // The conversion of chunk k + 1 runs on its own high-priority stream beside the accumulation of chunk k: its threads are
+    // latency-bound (one serial inversion chain per 64 points), the accumulate kernel is pipe-bound, together they fill the SMs.
+    const char *conv_env = getenv("B200MSM_CONV_STREAM");
+    const bool conv_async = !(conv_env && atoi(conv_env) == 0);
+    cudaStream_t cs = conv_async ? ctx->conv_stream : ctx->stream;
+    if (conv_async) CK(cudaStreamWaitEvent(cs, ctx->ev_free[0], 0));
     uint64_t k = 0;
     int used = 0;
     for (int ch = 0; ch < nch; ch++) {
@@ -797,11 +808,12 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
             if (k >= 2) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_raw_free[b], 0));
             rc = h2d(ctx, ctx->raw_buf[b], bases + s * stride, (size_t)(cnt * stride), ctx->copy_stream); if (rc) return rc;
             CK(cudaEventRecord(ctx->ev_raw_copied[b], ctx->copy_stream));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_raw_copied[b], 0));
-            LaunchCold<C>::convert_points(ctx->stream, ctx->raw_buf[b], (uint32_t)cnt, (uint32_t)stride, ctx->sw_buf, ctx->infmask + s / 32);
-            LaunchCold<C>::make_entries(ctx->stream, ctx->sw_buf, (uint32_t)cnt, ctx->tables + s * ctx->entry_bytes, ctx->acc_mix == 0);
-            CK(cudaEventRecord(ctx->ev_raw_free[b], ctx->stream));
+            CK(cudaStreamWaitEvent(cs, ctx->ev_raw_copied[b], 0));
+            LaunchCold<C>::convert_points(cs, ctx->raw_buf[b], (uint32_t)cnt, (uint32_t)stride, ctx->sw_buf, ctx->infmask + s / 32);
+            LaunchCold<C>::make_entries(cs, ctx->sw_buf, (uint32_t)cnt, ctx->tables + s * ctx->entry_bytes, ctx->acc_mix == 0);
+            CK(cudaEventRecord(ctx->ev_raw_free[b], cs));
         }
+        if (conv_async) { CK(cudaEventRecord(ctx->ev_conv, cs)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_conv, 0)); }
         rc = h2d(ctx, ctx->scal_buf[0] + first * 32, scalars + first * 32, (size_t)(end - first) * 32, ctx->copy_stream); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_chunk[used], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[used], 0));

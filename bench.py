@@ -316,11 +316,11 @@ def main():
             contest = {"skipped": str(ex)[:120]}
 
     # ---- arkworks' own call shape (VariableBaseMSM::multi_scalar_mul: bases AND scalars from host memory, no context, no
-    # table precompute), reported beside the headline; N = 1 only, 2^24 points (1.5 GiB of bases) at most
+    # table precompute), reported beside the headline at the headline size; N = 1 only
     one_call = None
     if world == 1 and not args.no_e2e:
         try:
-            m = min(n_local, 1 << 24)
+            m = n_local
             hb = eng.get_bases(0, m)                                   # uint8[m, 96]: x, y in arkworks' Montgomery form
             hs = host_scal.numpy()[:m * 32]
             V = M.VariableBaseMSM

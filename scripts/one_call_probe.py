@@ -28,10 +28,12 @@ hs_pageable = hs.copy()
 logs = KA.base_logs(n, SEED, 0, 1 << 15)
 r_mod = O.constants(0)["r"]
 V = M.VariableBaseMSM
-for lg in [x for x in (16, 20, 22, 24, 26) if x <= max_lg]:
+sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (16, 20, 22, 24, 26)
+variants = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else (0, 1, 2, 8)
+for lg in [x for x in sizes if x <= max_lg]:
     m = 1 << lg
     exp = KA.expected_affine(O, 0, KA.dot_mod_r(hs[:m * 32].reshape(m, 32), logs[:m], r_mod))
-    for chunks in ((0,) if lg < 22 else (0, 1, 2, 8)):
+    for chunks in ((0,) if lg < 22 else variants):
         for pinned in ((True, False) if chunks == 0 else (True,)):
             if chunks: os.environ["B200MSM_HOST_CHUNKS"] = str(chunks)
             else: os.environ.pop("B200MSM_HOST_CHUNKS", None)

@@ -428,7 +428,7 @@ def test_fp64_pipe_accumulator_flavour(M, oracle, monkeypatch):
     e.close()
 
 
-def test_one_call_variable_base_msm(M, oracle, golden_instances):
+def test_one_call_variable_base_msm(M, oracle, golden_instances, monkeypatch):
     """arkworks' own call shape, VariableBaseMSM::multi_scalar_mul(bases, scalars), through b200msm_variable_base_msm:
     golden instances, min(len) truncation, the empty MSM, sizes changing between calls on the cached context, the snarkVM
     dispatcher name and upstream sppark's 96-byte mult_pippenger."""
@@ -461,6 +461,16 @@ def test_one_call_variable_base_msm(M, oracle, golden_instances):
     s2 = O.gen_scalars(512, seed=93)
     got = M.multi_scalar_mult_blst(np.ascontiguousarray(q[:, :96]), s2)
     assert np.array_equal(O.jac_to_affine(got), O.jac_to_affine(O.ark_msm(q, s2)))
+    # the call split into 3 chunks (its default only from 2^21 points), with and without the conversion stream
+    for conv in ("1", "0"):
+        V.release()
+        monkeypatch.setenv("B200MSM_HOST_CHUNKS", "3")
+        monkeypatch.setenv("B200MSM_CONV_STREAM", conv)
+        assert np.array_equal(O.jac_to_affine(V.multi_scalar_mul(pts, sc)), exp), conv
+        assert np.array_equal(O.jac_to_affine(V.multi_scalar_mul(pts[:m], sc[:m])), exp_m), conv
+    V.release()
+    monkeypatch.delenv("B200MSM_HOST_CHUNKS")
+    monkeypatch.delenv("B200MSM_CONV_STREAM")
     # second curve through the same entry point
     p381, s381 = O.gen_points(700, seed=94, curve=1), O.gen_scalars(700, seed=95, curve=1)
     got = V.multi_scalar_mul(p381, s381, curve=M.BLS12_381)
