@@ -70,6 +70,7 @@ def lib():
     L.mult_pippenger.argtypes = [vp, vp, sz, vp]
     L.mult_pippenger.restype = _RustError
     L.b200msm_get_info.argtypes = [vp, ctypes.POINTER(u64)]
+    L.b200msm_plan_info.argtypes = [i32, u64, u64, i32, i32, i32, ctypes.POINTER(u64)]
     L.b200msm_get_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.b200msm_reset_stage_stats.argtypes = [vp]
     L.b200msm_get_stage_ms_sum.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(u64)]
@@ -97,7 +98,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
-    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info",
+    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info", "b200msm_plan_info",
     "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "b200msm_test_grp_op", "mult_pippenger_init", "mult_pippenger_inf",
     "mult_pippenger_free", "b200msm_variable_base_msm", "b200msm_variable_base_release", "mult_pippenger", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
 ]
@@ -365,6 +366,16 @@ class Engine:
         a = (ctypes.c_float * 6)()
         self._ck(lib().b200msm_get_stage_ms(self.h, a), "get_stage_ms")
         return dict(zip(self.STAGES, [float(v) for v in a]))
+
+
+def plan_info(n, curve=BLS12_377, free_bytes=170 << 30, window_bits=0, tables=0, chunks=1):
+    """The window plan for n points (host arithmetic only; works without a GPU)."""
+    a = (ctypes.c_uint64 * 8)()
+    rc = lib().b200msm_plan_info(curve, n, free_bytes, window_bits, tables, chunks, a)
+    if rc != 0:
+        raise MsmError(f"b200msm_plan_info: {rc}")
+    keys = ("n", "window_bits", "windows", "tables", "folded_windows", "buckets", "table_bytes", "refs")
+    return dict(zip(keys, [int(v) for v in a]))
 
 
 def test_fp_op(curve, op, a, b=None):

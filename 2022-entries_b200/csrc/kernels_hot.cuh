@@ -6,6 +6,7 @@
 #pragma once
 #include "kernels_util.cuh"
 #include "launch.h"
+#include "digits.cuh"
 
 namespace b200msm {
 
@@ -18,76 +19,6 @@ namespace b200msm {
 //   window w is served from base table j = w / F (holding 2^(c*F*j) P) into folded window f = w % F:
 //   bucket key = f * 2^(c-1) + |d| - 1,  point reference = j*N + i, bit 31 = negate.
 // PASS 0 counts keys; PASS 1 takes a slot in the bucket's list (cursor pre-loaded with the bucket offsets).
-template <class C> struct ScalarOps {
-    // s >= k*r ?  s -= k*r   (k*r must fit 256 bits)
-    template <int K> __device__ static void csub_kr(uint32_t (&s)[8]) {
-        uint32_t kr[8];
-        uint64_t carry = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { uint64_t t = (uint64_t)C::r(i) * K + carry; kr[i] = (uint32_t)t; carry = t >> 32; }
-        uint32_t t[8];
-        uint32_t borrow = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint64_t d = (uint64_t)s[i] - kr[i] - borrow;
-            t[i] = (uint32_t)d;
-            borrow = (uint32_t)(d >> 63);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = borrow ? s[i] : t[i];
-    }
-    __device__ static void mod_r(uint32_t (&s)[8]) {
-        if (C::SCALAR_BITS <= 253) { csub_kr<8>(s); csub_kr<4>(s); }
-        csub_kr<2>(s);
-        csub_kr<1>(s);
-    }
-    // returns true when s was replaced by r - s
-    __device__ static bool fold_top_bit(uint32_t (&s)[8]) {
-        const int tb = C::SCALAR_BITS - 1;
-        if (!((s[tb >> 5] >> (tb & 31)) & 1)) return false;
-        uint32_t borrow = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            uint64_t d = (uint64_t)C::r(i) - s[i] - borrow;
-            s[i] = (uint32_t)d;
-            borrow = (uint32_t)(d >> 63);
-        }
-        return true;
-    }
-};
-
-// walks the signed digits of scalar i (the scalar of base number gi): fn(bucket key, point reference) for every
-// non-zero digit
-template <class C, int MAXW = 0, class FN>
-__device__ __forceinline__ void for_each_digit(const uint32_t *__restrict__ scalars, uint32_t i, uint32_t gi, uint32_t table_stride, int c, int W, int F, FN fn) {
-    uint32_t s[9];
-    {
-        const uint4 *p = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
-        uint4 lo = __ldg(p), hi = __ldg(p + 1);
-        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-    }
-    uint32_t(&s8)[8] = reinterpret_cast<uint32_t(&)[8]>(s);
-    if (s[7] >= C::r(7)) ScalarOps<C>::mod_r(s8);      // top word below r's: already reduced (every harness scalar is)
-    bool neg = ScalarOps<C>::fold_top_bit(s8);
-    s[8] = 0;
-    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
-    uint32_t carry = 0;
-#pragma unroll
-    for (int w = 0; w < (MAXW > 0 ? MAXW : W); w++) {       // MAXW > 0: compile-time trip count, so fn may index registers by w
-        if (MAXW > 0 && w >= W) break;
-        int pos = w * c;
-        int wi = pos >> 5, sh = pos & 31;
-        uint64_t v = (uint64_t)s[wi] | ((uint64_t)s[wi + 1 > 8 ? 8 : wi + 1] << 32);
-        uint32_t d = ((uint32_t)(v >> sh) & mask) + carry;
-        bool flip = d > half;
-        if (flip) d = (1u << c) - d;
-        carry = flip ? 1u : 0u;
-        if (d == 0) continue;
-        if constexpr (MAXW > 0) fn(w, (uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + gi) | ((neg != flip) ? 0x80000000u : 0u));
-        else fn((uint32_t)(w % F) * half + d - 1, ((uint32_t)(w / F) * table_stride + gi) | ((neg != flip) ? 0x80000000u : 0u));
-    }
-}
-
 template <class C, int PASS>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ scalars, const uint32_t *__restrict__ infmask,
                                                 uint32_t n, uint32_t first, uint32_t table_stride, int c, int W, int F,

@@ -705,6 +705,21 @@ int b200msm_sync(b200msm_ctx *ctx) {
     return 0;
 }
 
+// The window plan alone (pure host arithmetic, no device needed): what a context created with (window_bits, tables) would
+// choose for n points with free_bytes of device memory, the reduction summing over `chunks` chunks.
+int b200msm_plan_info(int curve, uint64_t n, uint64_t free_bytes, int window_bits, int tables, int chunks, uint64_t info[8]) {
+    if ((curve != 0 && curve != 1) || n == 0 || n >= (1ull << 31) || !info || window_bits < 0 || window_bits > 26 || (window_bits > 0 && window_bits < 2) ||
+        tables < 0 || chunks < 1 || chunks > 8) return -1;
+    b200msm_ctx tmp;
+    tmp.curve = curve; tmp.req_c = window_bits; tmp.req_tables = tables; tmp.plan_chunks = chunks;
+    tmp.entry_bytes = curve == 0 ? LaunchCold<Bls12_377>::entry_bytes() : LaunchCold<Bls12_381>::entry_bytes();
+    choose_plan(&tmp, n, (size_t)free_bytes);
+    info[0] = n; info[1] = tmp.c; info[2] = tmp.W; info[3] = tmp.T; info[4] = tmp.F; info[5] = tmp.nbuckets;
+    info[6] = (uint64_t)tmp.T * n * tmp.entry_bytes;      // bytes of base tables
+    info[7] = (uint64_t)tmp.W * n;                        // point references per MSM
+    return 0;
+}
+
 int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]) {
     if (!ctx || !info) return -1;
     info[0] = ctx->n; info[1] = ctx->c; info[2] = ctx->W; info[3] = ctx->T; info[4] = ctx->F; info[5] = ctx->nbuckets; info[6] = ctx->lmax; info[7] = ctx->launches;

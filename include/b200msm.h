@@ -95,6 +95,10 @@ int b200msm_variable_base_release(void);
  * buckets, Lmax, kernel launches of the last MSM.  stage_ms[0..5] = digits+histogram, scan+scatter, pieces,
  * accumulate, bucket reduce, finalize (CUDA events on the context's stream; valid after b200msm_sync). */
 int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]);
+/* The window plan by itself, without a device: what b200msm_create(window_bits, tables) + set_bases(n) would choose with
+ * free_bytes of device memory, the bucket reduction summing over `chunks` chunks (1 for the resident-bases calls).
+ * info[0..7] = n, window bits c, windows W, tables T, folded windows F, buckets, bytes of base tables, point references. */
+int b200msm_plan_info(int curve, uint64_t n, uint64_t free_bytes, int window_bits, int tables, int chunks, uint64_t info[8]);
 int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]);
 /* The same six stage times summed over the MSMs run since b200msm_reset_stage_stats (at most the last 32 are kept);
  * *steps = how many MSMs the sums cover.  bench.py derives the per-launch duration of the accumulate kernel from it. */

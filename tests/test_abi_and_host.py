@@ -102,3 +102,42 @@ def test_c_harness_links_and_fails_loudly_without_gpu(M):
         pytest.skip("CUDA device present: the GPU suite runs the harness for real")
     p = subprocess.run([exe, "8"], capture_output=True, text=True)
     assert p.returncode == 2 and "no CPU path" in p.stderr
+
+
+def test_window_plan_invariants_and_headline_choice(M):
+    """choose_plan (csrc/msm.cu) through b200msm_plan_info, no device: invariants over sizes 2^0..2^30, both curves, memory
+    budgets and forced parameters; and the plans DESIGN.md quotes."""
+    bits = {0: 253, 1: 255}
+    for curve in (0, 1):
+        for lg in list(range(0, 31, 2)) + [23, 25, 27]:
+            n = 1 << lg
+            if n >= 1 << 31:
+                continue
+            for free in (8 << 30, 40 << 30, 170 << 30):
+                for wb, tb, ch in ((0, 0, 1), (0, 1, 1), (0, 1, 4), (0, 3, 1), (7, 0, 1), (16, 1, 2), (23, 0, 1)):
+                    p = M.plan_info(n, curve, free, wb, tb, ch)
+                    c, W, T, F = p["window_bits"], p["windows"], p["tables"], p["folded_windows"]
+                    assert 2 <= c <= 26 and (wb == 0 or c == wb)
+                    assert W == -(-bits[curve] // c) and W * c >= bits[curve]
+                    assert 1 <= T <= W and T * F >= W and (T - 1) * F < W          # every window has a table, no empty table
+                    assert tb == 0 or T <= tb
+                    assert p["buckets"] == F << (c - 1) and p["buckets"] <= 1 << 27
+                    assert T == 1 or T * n < 1 << 31                               # 31-bit point references
+                    assert T == 1 or p["table_bytes"] <= 0.72 * free               # tables fit the memory budget
+                    assert p["refs"] == W * n
+    # the headline plan (DESIGN.md section 3): 2^26 points on one B200 fold all 11 windows into one through 11 tables
+    p = M.plan_info(1 << 26, 0, 170 << 30)
+    assert (p["window_bits"], p["windows"], p["tables"], p["folded_windows"], p["buckets"]) == (23, 11, 11, 1, 1 << 22)
+    assert p["table_bytes"] == 11 * (1 << 26) * 144
+    # sharded over 8 GPUs the plan is re-derived for n / 8; the one-call form is one table with the chunked reduction charged
+    p = M.plan_info(1 << 23, 0, 170 << 30)
+    assert (p["window_bits"], p["tables"], p["folded_windows"]) == (23, 11, 1)
+    p = M.plan_info(1 << 26, 0, 170 << 30, 0, 1, 4)
+    assert (p["window_bits"], p["windows"], p["tables"], p["folded_windows"]) == (20, 13, 1, 13)
+    p = M.plan_info(1 << 24, 1, 170 << 30)
+    assert (p["window_bits"], p["windows"], p["tables"]) == (22, 12, 12)           # BLS12-381 at 2^24 (profiles/r01_sweep.txt)
+    # 2^28: 38.7 GB per table -> 3 tables, 4 folded windows
+    p = M.plan_info(1 << 28, 0, 170 << 30)
+    assert (p["window_bits"], p["tables"], p["folded_windows"]) == (23, 3, 4)
+    with pytest.raises(M.MsmError):
+        M.plan_info(0)

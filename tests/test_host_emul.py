@@ -292,3 +292,67 @@ def test_copy_pool_parallel_range_copy():
     for threads in (1, 3, 8, 16):
         p = subprocess.run([exe, str(threads)], capture_output=True, text=True, timeout=120)
         assert p.returncode == 0 and p.stdout.strip() == "ok", (threads, p.stdout, p.stderr)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a4 on the host: csrc/digits.cuh (the arithmetic of k_digits / k_digits_bin) against Python integers
+@pytest.fixture(scope="module")
+def digits():
+    so = os.path.join(HERE, "digits_emul.so")
+    src = os.path.join(HERE, "digits_emul.cpp")
+    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("digits.cuh", "fp.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+    L = ctypes.CDLL(so)
+    vp, sz, i32, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32
+    L.emul_digits.argtypes = [i32, vp, sz, u32, u32, i32, i32, i32, i32, vp, vp, vp, vp]
+    return L
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_signed_digit_decomposition_recomposes(digits, curve):
+    """For every window width c = 2..26 and table counts T in {1, 3, W}: the (key, reference) pairs of a scalar name each
+    window at most once, stay inside the bucket and table ranges, and  sum +-d_w 2^(c w) = s (mod r)  with the sign carried by
+    bit 31 of the reference -- for random scalars, scalars at and above r (reduced first) and the top-bit fold."""
+    from oracle import oracle as O
+    r = O.constants(curve)["r"]
+    bits = 253 if curve == 0 else 255
+    rng = np.random.default_rng(5 + curve)
+    vals = [0, 1, 2, r - 1, r, r + 1, (r - 1) // 2, (r + 1) // 2, (1 << (bits - 1)) - 1, 1 << (bits - 1), (1 << (bits - 1)) + 1,
+            (1 << bits) - 1, (1 << 256) - 1, 2 * r - 1, 2 * r, 2 * r + 5]
+    if curve == 0:
+        vals += [13 * r + 7, 8 * r, 4 * r - 1]                      # 2^256 < 14 r on BLS12-377
+    vals += [int.from_bytes(rng.bytes(32), "little") % r for _ in range(200)]
+    vals += [int.from_bytes(rng.bytes(32), "little") for _ in range(40)]        # unreduced 256-bit values
+    vals = [v for v in vals if v < (1 << 256)]
+    n = len(vals)
+    sc = np.zeros((n, 8), np.uint32)
+    for i, v in enumerate(vals):
+        sc[i] = np.frombuffer(int(v).to_bytes(32, "little"), np.uint32)
+    first, stride = 1000, 1 << 20
+    keys, refs, wins = np.zeros((n, 32), np.uint32), np.zeros((n, 32), np.uint32), np.zeros((n, 32), np.int32)
+    counts = np.zeros(n, np.int32)
+    for c in range(2, 27):
+        W = (bits + c - 1) // c
+        for T in sorted({1, min(3, W), W}):
+            F = (W + T - 1) // T
+            half = 1 << (c - 1)
+            for maxw16 in ((0, 1) if W <= 16 else (0,)):
+                if W > 32:
+                    continue                                         # the emulation buffers hold 32 pairs per scalar
+                digits.emul_digits(curve, _p(sc), n, first, stride, c, W, F, maxw16, _p(keys), _p(refs), _p(wins), _p(counts))
+                for i, v in enumerate(vals):
+                    total, seen = 0, set()
+                    for k in range(counts[i]):
+                        key, ref = int(keys[i, k]), int(refs[i, k])
+                        f, d = divmod(key, half)
+                        d += 1
+                        neg, idx = ref >> 31, ref & 0x7FFFFFFF
+                        j, gi = divmod(idx, stride)
+                        w = j * F + f
+                        assert gi == first + i and f < F and j < T and w < W and 1 <= d <= half and w not in seen, (c, T, v)
+                        if maxw16:
+                            assert int(wins[i, k]) == w
+                        seen.add(w)
+                        total += (-d if neg else d) << (c * w)
+                    assert total % r == v % r, (curve, c, T, hex(v))
