@@ -139,7 +139,7 @@ def run_reference(args):
     cores = ark_threads(O, 1 << ls)
     sample = f"2^{ls} points per step (harness-shaped: 2^10 distinct bases replicated, uniform scalars), arkworks window rule c={O.window_bits(1 << ls)}"
     line = {"impl": "reference", "metric": METRIC.format(lg=lg), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (377-bit modular integer)",
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 (377-bit modular integers as 6 x u64 Montgomery limbs, unsigned __int128 products)",
             "data": "synthetic", "config": {"workload": WORKLOAD.format(lg=lg), "log_n": lg, "cpu_sample_log_n": ls},
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
