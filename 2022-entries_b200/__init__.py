@@ -3,7 +3,7 @@
 The reference harness is Rust (`multi_scalar_mult_init` / `multi_scalar_mult`,
 P1A/storswiftlabs/src/lib.rs:43-98, P1A/yrrid/src/lib.rs:38-90; P1A = open-division/prize1-msm/prize1a-msm-gpu);
 this image has no Rust toolchain, so the same two calls are mirrored here over the same `extern "C"` symbols
-(include/b200msm.h).  The Rust binding a maintainer would add is in INTEGRATION.md and rust/.
+(include/b200msm.h).  The Rust binding a maintainer would add is in INTEGRATION.md.
 
 Everything here is plumbing over `libb200msm.so` (hand-written sm_100a CUDA).  There is no CPU path: if the
 library is missing or no CUDA device is usable, calls raise.
