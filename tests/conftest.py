@@ -43,3 +43,16 @@ def golden_instances(oracle):
         except Exception:
             pass
     return [dict(aff=affs[k], scalars=inst[k][1], result=inst[k][2]) for k in range(len(inst))]
+
+
+@pytest.fixture(scope="session")
+def bls381_small_multiples(oracle):
+    """The ten BLS12-381 G1 points of the reference's wasm tests (tests/golden/bls12_381_small_multiples.json) as arkworks
+    G1Affine records (uint8[10, 104], Montgomery) and the k with point = k * G."""
+    import json
+    d = json.load(open(os.path.join(GOLDEN, "bls12_381_small_multiples.json")))
+    aff = np.zeros((len(d["points"]), 104), np.uint8)
+    for i, (x, y) in enumerate(d["points"]):
+        canon = np.frombuffer(int(x, 16).to_bytes(48, "little") + int(y, 16).to_bytes(48, "little"), np.uint8)
+        aff[i, :96] = oracle.fp_convert(canon, True, curve=1).reshape(-1)
+    return aff, d["multiples_of_first_point"]

@@ -11,6 +11,12 @@ prize-7 mobile harness into tests/golden/ and records their sha256:
   /root/reference/open-division/prize7-msm-mobile/yyteam/mobileMSM/app/src/main/assets/zero-points-test/
       {points,scalars}: 256 points all flagged infinity (edge case; expected result = infinity).
 
+  /root/reference/open-division/prize4-msm-wasm/Manta-Network/submission/wasmcurves-optimized/test/batchAffine.js
+      "g1m add is correct." (l.732-745): ten BLS12-381 G1 points in canonical (non-Montgomery) affine form that the
+      reference's wasm tests feed to its group law -- the only BLS12-381 G1 constants the reference holds besides the
+      generator.  They are k*G for k = 1, 2, 3, 5, 4, 6, 7, 8, 9, 9 (established below with affine chord-and-tangent
+      arithmetic on Python integers, independent of oracle/); written to bls12_381_small_multiples.json.
+
 These are DATA fixtures produced by the reference's own oracle (arkworks), not reference sources.
 Format: repeat { u64 LE n ; n x 48-byte compressed G1Affine } for points,
 repeat { u64 LE n ; n x 32-byte LE canonical scalar } for scalars, one 48-byte compressed point per
@@ -19,6 +25,7 @@ instance for result.
 import hashlib
 import json
 import os
+import re
 import shutil
 
 REF = "/root/reference/open-division/prize7-msm-mobile"
@@ -33,7 +40,48 @@ FILES = {
 }
 
 
+WASM_TEST = "/root/reference/open-division/prize4-msm-wasm/Manta-Network/submission/wasmcurves-optimized/test/batchAffine.js"
+P381 = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
+
+def _affine_add(P, Q, p):
+    if P is None or Q is None:
+        return P or Q
+    (x1, y1), (x2, y2) = P, Q
+    if x1 == x2:
+        if (y1 + y2) % p == 0:
+            return None
+        lam = 3 * x1 * x1 * pow(2 * y1, -1, p) % p
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, -1, p) % p
+    x3 = (lam * lam - x1 - x2) % p
+    return x3, (lam * (x1 - x3) - y1) % p
+
+
+def import_bls12_381_points():
+    src = open(WASM_TEST).read()
+    blk = src[src.index('it("g1m add is correct."'):]
+    blk = blk[:blk.index("let numPoints")]
+    nums = [int(h, 16) for h in re.findall(r"0x([0-9a-f]{80,96})n", blk)]
+    assert len(nums) == 20
+    pts = [(nums[2 * i], nums[2 * i + 1]) for i in range(10)]
+    multiples, acc, seen = [None] * 10, None, {}
+    for k in range(1, 33):
+        acc = _affine_add(acc, pts[0], P381)
+        seen[acc] = k
+    multiples = [seen[q] for q in pts]                      # KeyError = not a small multiple of the first point
+    assert multiples == [1, 2, 3, 5, 4, 6, 7, 8, 9, 9]
+    assert all((y * y - x * x * x - 4) % P381 == 0 for x, y in pts)
+    out = {"source": WASM_TEST.replace("/root/reference/", "") + ' ("g1m add is correct.", input points)',
+           "form": "canonical affine (x, y), big-endian hex, not Montgomery", "multiples_of_first_point": multiples,
+           "points": [["%096x" % x, "%096x" % y] for x, y in pts]}
+    with open(os.path.join(HERE, "bls12_381_small_multiples.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    return out
+
+
 def main():
+    import_bls12_381_points()
     manifest = {}
     for dst, src in FILES.items():
         out = os.path.join(HERE, dst)

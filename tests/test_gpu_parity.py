@@ -539,3 +539,23 @@ def test_staged_upload_of_pageable_arrays(M, oracle, monkeypatch):
     got = M.VariableBaseMSM.multi_scalar_mul(hb, sc, stride=96)
     assert np.array_equal(O.jac_to_affine(got)[0], KA.expected_affine(O, 0, t))
     M.VariableBaseMSM.release()
+
+
+def test_bls12_381_reference_points_through_the_engine(M, oracle, bls381_small_multiples):
+    """The BLS12-381 G1 points the reference holds (k * G, k = 1, 2, 3, 5, 4, 6, 7, 8, 9, 9; tests/golden/
+    bls12_381_small_multiples.json) as bases, replicated as the harness replicates its bases: the engine's MSM equals the
+    closed form (sum k_i s_i) G and the oracle's MSM."""
+    import known_answer as KA
+    O = oracle
+    aff, ks = bls381_small_multiples
+    reps = 64
+    pts = np.tile(aff, (reps, 1))
+    n = len(pts)
+    sc = O.gen_scalars(n, seed=382, curve=1)
+    t = sum(ks[i % len(ks)] * int.from_bytes(sc[i].tobytes(), "little") for i in range(n)) % O.constants(1)["r"]
+    eng = M.Engine(M.BLS12_381)
+    eng.set_bases(pts)
+    got = _engine_result(M, O, eng, sc, 1)
+    eng.close()
+    assert np.array_equal(got, KA.expected_affine(O, 1, t))
+    assert np.array_equal(got, O.jac_to_affine(O.ark_msm(pts, sc, 1), 1)[0])

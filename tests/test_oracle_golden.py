@@ -125,3 +125,24 @@ def test_harness_fixture_files_roundtrip(oracle, tmp_path):
     assert os.path.getsize(tmp_path / "points.bin") == 8 + 48 * n and os.path.getsize(tmp_path / "scalars.bin") == 8 + 32 * n * batches
     b2, pts2, sc2, res2 = HD.load(oracle, str(tmp_path))
     assert b2 == batches and np.array_equal(pts2, pts) and np.array_equal(sc2, sc) and np.array_equal(res2, res)
+
+
+def test_bls12_381_small_multiples_of_the_generator(oracle, bls381_small_multiples):
+    """BLS12-381 has no MSM known-answer vector in the reference; what it does hold are ten G1 points in the wasm entry's
+    group-law tests (open-division/prize4-msm-wasm/Manta-Network/.../test/batchAffine.js:732-745), k * G for
+    k = 1, 2, 3, 5, 4, 6, 7, 8, 9, 9.  Both oracles must reproduce every one from the generator, and an MSM over them
+    must equal the closed form (sum k_i s_i) G."""
+    import known_answer as KA
+    aff, ks = bls381_small_multiples
+    c = oracle.constants(1)
+    assert oracle.on_curve(aff, 1)
+    assert int.from_bytes(aff[0, :48].tobytes(), "little") == c["gx"] and int.from_bytes(aff[0, 48:96].tobytes(), "little") == c["gy"]
+    for i, k in enumerate(ks):
+        assert np.array_equal(KA.expected_affine(oracle, 1, k), aff[i]), k            # C oracle: k * G by double-and-add
+        q = RB.mul(k, (RB.CURVES[1]["gx"], RB.CURVES[1]["gy"]), RB.CURVES[1]["p"])      # Python big integers, affine law
+        assert RB.to_mont_affine_bytes(q, 1) == aff[i].tobytes(), k
+    sc = oracle.gen_scalars(len(ks), seed=381, curve=1)
+    t = sum(k * int.from_bytes(sc[i].tobytes(), "little") for i, k in enumerate(ks)) % c["r"]
+    exp = KA.expected_affine(oracle, 1, t)
+    assert np.array_equal(oracle.jac_to_affine(oracle.ark_msm(aff, sc, 1), 1)[0], exp)
+    assert np.array_equal(oracle.jac_to_affine(oracle.naive_msm(aff, sc, 1), 1)[0], exp)
