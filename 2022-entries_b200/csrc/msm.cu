@@ -258,8 +258,8 @@ static int h2d(b200msm_ctx *ctx, void *dst, const void *src, size_t bytes, cudaS
     if (direct) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0; }
     if (!ctx->pool) {
         for (int i = 0; i < 2; i++) {
-            CK(cudaHostAlloc((void **)&ctx->slot[i], b200msm_ctx::SLOT_BYTES, cudaHostAllocDefault));
-            CK(cudaEventCreateWithFlags(&ctx->slot_ev[i], cudaEventDisableTiming));
+            if (!ctx->slot[i]) CK(cudaHostAlloc((void **)&ctx->slot[i], b200msm_ctx::SLOT_BYTES, cudaHostAllocDefault));      // (a retry after a failed first attempt)
+            if (!ctx->slot_ev[i]) CK(cudaEventCreateWithFlags(&ctx->slot_ev[i], cudaEventDisableTiming));
         }
         int p = (int)std::thread::hardware_concurrency() / 2;
         if (const char *e = getenv("B200MSM_COPY_THREADS")) p = atoi(e);
