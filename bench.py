@@ -309,8 +309,19 @@ def main():
             t0 = time.perf_counter()
             r4 = M.multi_scalar_mult(hctx, None, sc4)
             dt = time.perf_counter() - t0
-            contest = {"batches": 4, "ms_total": dt * 1e3, "ms_per_msm": dt * 1e3 / 4, "results": int(r4.shape[0]),
+            contest = {"batches": 4, "ms_total": dt * 1e3, "ms_per_msm": dt * 1e3 / 4, "results": int(r4.shape[0]), "scalars": "pinned host memory",
                        "published_A40_ms_total": "2200-2300 (combined-top-solutions README; other hardware)"}
+            try:                         # the same call with the scalars in pageable memory, which is what a Rust Vec is
+                pageable = np.empty_like(sc4)
+                pageable[:] = sc4
+                M.multi_scalar_mult(hctx, None, pageable)
+                t0 = time.perf_counter()
+                r4p = M.multi_scalar_mult(hctx, None, pageable)
+                contest["pageable_ms_total"] = (time.perf_counter() - t0) * 1e3
+                contest["pageable_same_result"] = bool(np.array_equal(r4p, r4))
+                del pageable
+            except Exception as ex:
+                contest["pageable_skipped"] = str(ex)[:120]
             del host4
         except Exception as ex:          # pinned 8 GiB may not be available everywhere; the headline does not depend on it
             contest = {"skipped": str(ex)[:120]}
