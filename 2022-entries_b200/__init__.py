@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200msm.so")
+LIB_PATH = os.environ.get("B200MSM_LIB") or os.path.join(_HERE, "libb200msm.so")      # override: experiment builds (scripts/build_variants.py)
 BLS12_377, BLS12_381 = 0, 1
 BASES_HARNESS, BASES_DISTINCT = 0, 1
 AFFINE_BYTES, SCALAR_BYTES, PROJECTIVE_BYTES = 104, 32, 144
@@ -55,6 +55,7 @@ def lib():
     L.b200msm_last_error.argtypes = [vp]
     L.b200msm_last_error.restype = ctypes.c_char_p
     L.b200msm_set_stream.argtypes = [vp, vp]
+    L.b200msm_set_bucket_arithmetic.argtypes = [vp, i32]
     L.b200msm_set_bases.argtypes = [vp, vp, u64, u64]
     L.b200msm_set_bases_generated.argtypes = [vp, u64, u64, i32, u64]
     L.b200msm_get_bases.argtypes = [vp, vp, u64, u64]
@@ -96,7 +97,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bases",
+    "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bucket_arithmetic", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
     "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info", "b200msm_plan_info",
     "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "b200msm_test_grp_op", "mult_pippenger_init", "mult_pippenger_inf",
@@ -299,6 +300,10 @@ class Engine:
 
     def set_stream(self, cuda_stream):
         self._ck(lib().b200msm_set_stream(self.h, ctypes.c_void_p(cuda_stream)), "set_stream")
+
+    def set_bucket_arithmetic(self, xyzz):
+        """xyzz=True: short-Weierstrass XYZZ buckets (complete on every on-curve point); False: the curve's default."""
+        self._ck(lib().b200msm_set_bucket_arithmetic(self.h, 1 if xyzz else 0), "set_bucket_arithmetic")
 
     def set_bases(self, points, stride=AFFINE_BYTES):
         pts = _as_u8(points, stride, "points")

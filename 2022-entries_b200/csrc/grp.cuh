@@ -15,6 +15,7 @@ template <class C> struct GrpXyzz {
     typedef affine_t entry_t;
     static constexpr int ENTRY_VEC = sizeof(affine_t) / 16;       // 7
     typedef xyzz_t acc_t;                                         // the accumulate kernel's register accumulator
+    static constexpr bool INF_ENTRIES = true;                     // a table entry (0, 0) stands for the point at infinity
     FP_HD static void set_inf(xyzz_t &a) { Ec<C>::set_inf(a); }
 #if defined(__CUDACC__)
     __device__ __forceinline__ static void acc_init(acc_t &a) { Ec<C>::set_inf(a); }
@@ -26,6 +27,8 @@ template <class C> struct GrpXyzz {
         uint4 *t = reinterpret_cast<uint4 *>(&pt);
 #pragma unroll
         for (int k = 0; k < ENTRY_VEC; k++) t[k] = st[k * stride];
+        // (0, 0): 2^(c F j) P at infinity for a base P of small even order (outside G1); lies on neither curve
+        if (F::is_literal_zero(pt.x) && F::is_literal_zero(pt.y)) return;
         if (negate) F::template neg<2>(pt.y, pt.y);
         Ec<C>::madd(acc, pt.x, pt.y);
     }
@@ -37,7 +40,8 @@ template <class C> struct GrpXyzz {
         return true;
     }
     // thread t converts src[t*GRP_BATCH ...] (short-Weierstrass affine, canonical) to entries: a copy here
-    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t, bool /*ark*/) {
+    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t, bool /*ark*/,
+                                        const uint32_t * /*infmask*/, uint32_t * /*bad*/) {
         for (uint32_t k = 0; k < GRP_BATCH; k++) {
             const uint32_t i = t * GRP_BATCH + k;
             if (i >= n) return;
@@ -56,6 +60,7 @@ template <class C> struct GrpTe {
     typedef te_entry_t entry_t;
     static constexpr int ENTRY_VEC = sizeof(te_entry_t) / 16;     // 9
     typedef ted_t acc_t;                                          // FP64-pipe accumulator (te.cuh TeD)
+    static constexpr bool INF_ENTRIES = false;                    // every entry is a finite point (unmappable bases are refused)
     FP_HD static void set_inf(xyzz_t &a) { Te<C>::set_inf(a); }
 #if defined(__CUDACC__)
     __device__ __forceinline__ static void acc_init(acc_t &a) { TeD<C>::set_inf(a); }
@@ -106,8 +111,11 @@ template <class C> struct GrpTe {
     }
     // Montgomery's trick over GRP_BATCH points: one inversion per thread.  A zero denominator (y = 0 or
     // s (x + 1) = -1: only for points outside G1, or the (0, 0) placeholder of a base flagged infinity, which the digit
-    // kernel never references) is replaced by 1 so that it cannot poison its batch.
-    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t, bool ark) {
+    // kernel never references) is replaced by 1 so that it cannot poison its batch; unless the base is flagged infinity
+    // (infmask: bit i = point i of src) it is COUNTED in *bad -- such a point has no image in this model and the host
+    // refuses the base set (msm.cu check_bad_entries) instead of returning a wrong sum.
+    __device__ static void make_entries(const affine_t *__restrict__ src, uint32_t n, entry_t *__restrict__ dst, uint32_t t, bool ark,
+                                        const uint32_t *__restrict__ infmask, uint32_t *__restrict__ bad) {
         const uint32_t base = t * GRP_BATCH;
         if (base >= n) return;
         const uint32_t cnt = n - base < GRP_BATCH ? n - base : GRP_BATCH;
@@ -119,7 +127,11 @@ template <class C> struct GrpTe {
             load_affine_plain(a, src + base + k);
             fp nu, nv, dv, den;
             Te<C>::map_prepare(nu, nv, dv, den, a.x, a.y);
-            if (F::is_zero(den)) F::set_one(den);
+            if (F::is_zero(den)) {
+                F::set_one(den);
+                const uint32_t i = base + k;
+                if (bad && !(infmask && (infmask[i >> 5] >> (i & 31)) & 1)) atomicAdd(bad, 1u);
+            }
             prefix[k] = acc;
             Ec<C>::mul_ni(acc, acc, den);
         }

@@ -206,7 +206,13 @@ __global__ void __launch_bounds__(128) k_convert_points(const uint8_t *__restric
         Ec<C>::from_abi_ni(o.x, ax);
         Ec<C>::from_abi_ni(o.y, ay);
         store_affine(table0 + i, o);
-        inf = stride > 96 && src[(size_t)i * stride + 96] != 0;
+        // infinity: the arkworks flag byte (records longer than 96 bytes), or x = y = 0 -- the encoding of the flag-less
+        // 96-byte blst_p1_affine records (sppark affine_t::is_inf, P1A/6block/sppark/ec/xyzz_t.hpp:44-45); (0, 0) is on
+        // neither curve, so the second test never misreads a finite point
+        uint32_t any = 0;
+#pragma unroll
+        for (int k = 0; k < 24; k++) any |= p[k];
+        inf = (stride > 96 && src[(size_t)i * stride + 96] != 0) || any == 0;
     }
     uint32_t bits = __ballot_sync(0xffffffffu, inf);
     if ((threadIdx.x & 31) == 0 && i < n) infmask[i >> 5] = bits;
@@ -226,8 +232,9 @@ __global__ void __launch_bounds__(128) k_export_points(const typename Grp<C>::en
 }
 // short-Weierstrass affine chunk -> table entries in the curve's bucket coordinates (grp.cuh)
 template <class C>
-__global__ void __launch_bounds__(128) k_make_entries(const affine_t *__restrict__ src, uint32_t n, typename Grp<C>::entry_t *__restrict__ dst, bool ark) {
-    Grp<C>::make_entries(src, n, dst, blockIdx.x * blockDim.x + threadIdx.x, ark);
+__global__ void __launch_bounds__(128) k_make_entries(const affine_t *__restrict__ src, uint32_t n, typename Grp<C>::entry_t *__restrict__ dst, bool ark,
+                                                      const uint32_t *__restrict__ infmask, uint32_t *__restrict__ bad) {
+    Grp<C>::make_entries(src, n, dst, blockIdx.x * blockDim.x + threadIdx.x, ark, infmask, bad);
 }
 // tmp[i] = 2^k * src[i]  (XYZZ, not normalised)
 template <class C>
@@ -242,10 +249,13 @@ __global__ void __launch_bounds__(128) k_double_n(const affine_t *__restrict__ s
     store_xyzz(tmp + i, q);
 }
 // XYZZ -> canonical affine with one inversion per BATCH points (Montgomery's trick on ZZZ).
-// A ZZZ of zero (only reachable from bases outside the prime-order subgroup) is replaced by 1 so it cannot poison
-// its batch; that entry's output is meaningless, as the contract (bases in G1) allows.
+// A ZZZ of zero -- 2^k P at infinity: P is a base flagged infinity, or a base outside the prime-order subgroup whose order
+// divides 2^k -- is replaced by 1 so it cannot poison its batch, and the point is written as (0, 0): the XYZZ mixed add
+// skips such entries (grp.cuh GrpXyzz::madd_staged), so that arithmetic stays exact for every on-curve base; the
+// twisted-Edwards arithmetic has no such entry and counts the base in *bad instead (unless infmask flags it).
 template <class C>
-__global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restrict__ tmp, uint32_t n, affine_t *__restrict__ dst) {
+__global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restrict__ tmp, uint32_t n, affine_t *__restrict__ dst,
+                                                         const uint32_t *__restrict__ infmask, uint32_t *__restrict__ bad) {
     typedef Fp<C> F;
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t base = t * NORM_BATCH;
@@ -260,7 +270,11 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restric
         uint2 *d = reinterpret_cast<uint2 *>(&z);
 #pragma unroll
         for (int v = 0; v < 7; v++) d[v] = s[v];
-        if (F::is_zero(z)) F::set_one(z);
+        if (F::is_zero(z)) {
+            F::set_one(z);
+            const uint32_t i = base + k;
+            if (!Grp<C>::INF_ENTRIES && bad && !(infmask && (infmask[i >> 5] >> (i & 31)) & 1)) atomicAdd(bad, 1u);
+        }
         prefix[k] = acc;
         Ec<C>::mul_ni(acc, acc, z);
     }
@@ -269,7 +283,8 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restric
     for (uint32_t k = cnt; k-- > 0;) {
         xyzz_t q;
         load_xyzz(q, tmp + base + k);
-        if (F::is_zero(q.zzz)) F::set_one(q.zzz);
+        const bool at_inf = F::is_zero(q.zzz);
+        if (at_inf) F::set_one(q.zzz);
         fp i1;
         Ec<C>::mul_ni(i1, inv, prefix[k]);      // 1 / ZZZ_k
         Ec<C>::mul_ni(inv, inv, q.zzz);         // drop ZZZ_k from the running inverse
@@ -282,6 +297,7 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const xyzz_t *__restric
         Ec<C>::mul_ni(o.y, q.y, i1);
         F::csub_p(o.x);
         F::csub_p(o.y);
+        if (at_inf) { F::set_zero(o.x); F::set_zero(o.y); }
         store_affine(dst + base + k, o);
     }
 }
@@ -385,7 +401,7 @@ __global__ void k_test_grp(int op, const affine_abi_t *a, const affine_abi_t *b,
     Ec<C>::from_abi_ni(sw[1][lane].x, b[srci].x); Ec<C>::from_abi_ni(sw[1][lane].y, b[srci].y);
     __syncthreads();
     // GRP_BATCH consecutive points per converting thread
-    if (lane < 64 / GRP_BATCH) { G::make_entries(sw[0], 64, ent[0], lane, false); G::make_entries(sw[1], 64, ent[1], lane, false); }
+    if (lane < 64 / GRP_BATCH) { G::make_entries(sw[0], 64, ent[0], lane, false, nullptr, nullptr); G::make_entries(sw[1], 64, ent[1], lane, false, nullptr, nullptr); }
     __syncthreads();
     if (i >= n) return;
     xyzz_t acc, other;

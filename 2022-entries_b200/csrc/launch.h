@@ -33,12 +33,12 @@ template <class C> struct LaunchCold {
     static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac);
     static void combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac);
     static void double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp);
-    static void batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst);
+    static void batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst, const uint32_t *infmask, uint32_t *bad);
     static void gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp);
     static void gen_scalars(cudaStream_t st, uint32_t n, uint64_t seed, uint32_t *out);
     static void convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask);
     static void export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst, bool ark);
-    static void make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark);
+    static void make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark, const uint32_t *infmask, uint32_t *bad);
     static size_t entry_bytes();
     static void test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps);
     static void generator(fp &gx, fp &gy);      // host: the curve generator in the device representation

@@ -23,8 +23,8 @@ template <class C> void LaunchCold<C>::combine(cudaStream_t st, const xyzz_t *pa
 template <class C> void LaunchCold<C>::double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp) {
     k_double_n<C><<<cdiv(n, 128), 128, 0, st>>>(src, n, k, tmp);
 }
-template <class C> void LaunchCold<C>::batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst) {
-    k_batch_normalize<C><<<cdiv(cdiv(n, NORM_BATCH), 128), 128, 0, st>>>(tmp, n, dst);
+template <class C> void LaunchCold<C>::batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst, const uint32_t *infmask, uint32_t *bad) {
+    k_batch_normalize<C><<<cdiv(cdiv(n, NORM_BATCH), 128), 128, 0, st>>>(tmp, n, dst, infmask, bad);
 }
 template <class C>
 void LaunchCold<C>::gen_points(cudaStream_t st, uint32_t first, uint32_t n, uint64_t seed, int mode, uint32_t distinct, const fp &gx, const fp &gy, xyzz_t *tmp) {
@@ -39,8 +39,8 @@ template <class C> void LaunchCold<C>::convert_points(cudaStream_t st, const uin
 template <class C> void LaunchCold<C>::export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst, bool ark) {
     k_export_points<C><<<cdiv(n, 128), 128, 0, st>>>((const typename Grp<C>::entry_t *)entries, n, dst, ark);
 }
-template <class C> void LaunchCold<C>::make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark) {
-    k_make_entries<C><<<cdiv(cdiv(n, GRP_BATCH), 128), 128, 0, st>>>(src, n, (typename Grp<C>::entry_t *)dst_entries, ark);
+template <class C> void LaunchCold<C>::make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark, const uint32_t *infmask, uint32_t *bad) {
+    k_make_entries<C><<<cdiv(cdiv(n, GRP_BATCH), 128), 128, 0, st>>>(src, n, (typename Grp<C>::entry_t *)dst_entries, ark, infmask, bad);
 }
 template <class C> size_t LaunchCold<C>::entry_bytes() { return sizeof(typename Grp<C>::entry_t); }
 template <class C> void LaunchCold<C>::test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps) {

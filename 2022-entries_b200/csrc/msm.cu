@@ -27,6 +27,14 @@ static thread_local std::string g_create_error;
     } while (0)
 
 
+// bucket arithmetic of a context: 0 = BLS12-377 twisted Edwards (default), 1 = BLS12-381 XYZZ, 2 = BLS12-377 XYZZ
+#define BY_GROUP(kind, ...)                                              \
+    switch (kind) {                                                      \
+    case 0: { typedef Bls12_377 C; __VA_ARGS__; } break;                 \
+    case 1: { typedef Bls12_381 C; __VA_ARGS__; } break;                 \
+    default: { typedef Bls12_377_sw C; __VA_ARGS__; } break;             \
+    }
+
 struct red_step_t {
     int kind;                 // 0: reduce_slices through the piece table, 1: reduce_slices, 2: block_sum
     const xyzz_t *in;
@@ -36,6 +44,7 @@ struct red_step_t {
 
 struct b200msm_ctx {
     int curve = 0, device = 0;
+    int kind = 0;             // BY_GROUP selector: curve, except 2 = BLS12-377 with XYZZ buckets (b200msm_set_bucket_arithmetic)
     int req_c = 0, req_tables = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, conv_stream = nullptr;   // conv: entry conversion of the one-call form (high priority)
     cudaEvent_t ev_conv = nullptr;
@@ -59,6 +68,7 @@ struct b200msm_ctx {
     uint8_t *tables = nullptr;          // T tables of n entries in the curve's bucket coordinates (grp.cuh)
     size_t entry_bytes = 0;
     uint32_t *infmask = nullptr;
+    uint32_t *bad = nullptr;            // bases without an image in the bucket coordinate system (counted by make_entries)
     uint32_t *counts = nullptr, *bucket_off = nullptr, *cursor = nullptr, *piece_off = nullptr;
     uint32_t *piece_start = nullptr, *piece_len = nullptr, *order = nullptr, *len_hist = nullptr, *len_cursor = nullptr;
     uint32_t *scan_tmp = nullptr, *refs = nullptr;
@@ -84,10 +94,14 @@ struct b200msm_ctx {
     uint64_t out_dev_cap = 0;
     std::vector<red_step_t> red_steps;
     fin_args_t fin;
-    static const int EV_RING = 32;
-    cudaEvent_t evr[EV_RING][7] = {};   // stage boundaries of the last EV_RING MSMs
-    uint64_t ev_steps = 0;              // MSMs recorded since the last stats reset
-    cudaEvent_t *ev = evr[0];           // the set the current / last MSM records into
+    // Stage boundaries: one event set per CHUNK (stages 0-3: digits, scatter, pieces, accumulate); the set of an MSM's
+    // last chunk also takes the reduction and finalize boundaries (ev_last = 6) and closes the MSM.  A plain MSM is one set.
+    static const int EV_RING = 64;
+    cudaEvent_t evr[EV_RING][7] = {};
+    uint8_t ev_last[EV_RING] = {};      // index of the last event recorded in the set (4 or 6)
+    uint64_t ev_sets = 0;               // sets recorded since the last stats reset
+    uint64_t ev_steps = 0;              // MSMs completed since the last stats reset
+    cudaEvent_t *ev = evr[0];           // the set the current chunk records into
     cudaEvent_t ev_copied[2] = {}, ev_free[2] = {};
 
     int fail(int code, const std::string &msg) {
@@ -97,10 +111,10 @@ struct b200msm_ctx {
         return code;
     }
     void free_plan() {
-        void *ptrs[] = {tables, infmask, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
+        void *ptrs[] = {tables, infmask, bad, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
                         scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1], bin_cursor, staging, raw_buf[0], raw_buf[1], sw_buf};
         for (void *p : ptrs) if (p) cudaFree(p);
-        tables = nullptr; infmask = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
+        tables = nullptr; infmask = nullptr; bad = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
         scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
         raw_buf[0] = raw_buf[1] = nullptr; sw_buf = nullptr; raw_cap = 0;
         red_steps.clear();
@@ -116,7 +130,7 @@ static int scalar_bits(int curve) { return curve == 0 ? Bls12_377::SCALAR_BITS :
 // window plan: choose c (window bits), T (tables) and F (folded windows) for n points.
 // cost model: W*n mixed adds (10 modmul) + 2 full adds (14 modmul) per bucket, buckets = F * 2^(c-1);
 // T limited by device memory (96 n bytes per table) and by the 31-bit point reference (T*n < 2^31).
-static void choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
+static bool choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
     const int sb = scalar_bits(ctx->curve);
     uint64_t tmax_mem = (uint64_t)((double)free_bytes * 0.72 / ((double)ctx->entry_bytes * (double)n));
     uint64_t tmax_ref = ((1ull << 31) - 1) / n;
@@ -136,12 +150,14 @@ static void choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
         double cost = 10.0 * (double)W * (double)n + red;
         if (cost < best) { best = cost; best_c = c; }
     }
+    if (best_c == 0) return false;      // every candidate needs more than 2^27 buckets (a forced window of 25 / 26 bits with few tables)
     ctx->c = best_c;
     ctx->W = (sb + best_c - 1) / best_c;
     int T = (int)(tmax < (uint64_t)ctx->W ? tmax : ctx->W);
     ctx->F = (ctx->W + T - 1) / T;
     ctx->T = (ctx->W + ctx->F - 1) / ctx->F;
     ctx->nbuckets = (uint32_t)ctx->F << (ctx->c - 1);
+    return true;
 }
 
 template <class T> static cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
@@ -151,7 +167,7 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     ctx->free_plan();
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    choose_plan(ctx, n, free_b);
+    if (!choose_plan(ctx, n, free_b)) return ctx->fail(-1, "window_bits / tables combination needs more than 2^27 buckets");
     ctx->n = n;
     ctx->max_refs = (uint64_t)ctx->W * n;
     if (ctx->max_refs >= (1ull << 32)) return ctx->fail(-1, "too many point references for 32-bit list offsets");
@@ -164,6 +180,8 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     const uint32_t nb = ctx->nbuckets;
     CK(dmalloc(&ctx->tables, (size_t)ctx->T * n * ctx->entry_bytes));
     CK(dmalloc(&ctx->infmask, (size_t)cdiv(n, 32) + 1));
+    CK(dmalloc(&ctx->bad, 1));
+    CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
     CK(dmalloc(&ctx->counts, (size_t)nb + 1));
     CK(dmalloc(&ctx->bucket_off, (size_t)nb + 1));
     CK(dmalloc(&ctx->cursor, (size_t)nb + 1));
@@ -296,16 +314,17 @@ static int scratch_alloc(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t cap) {
     return 0;
 }
 // sc.sw[0] holds cnt affine points starting at index `first`: emit their entries into every table
-template <class C> static void emit_tables(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t first, uint32_t cnt) {
+// infmask: the infinity bits of these cnt points (bit 0 = point `first`), or nullptr when none is at infinity
+template <class C> static void emit_tables(b200msm_ctx *ctx, table_scratch_t &sc, uint32_t first, uint32_t cnt, const uint32_t *infmask) {
     const size_t eb = ctx->entry_bytes;
     int cur = 0;
     for (int j = 0; j < ctx->T; j++) {
         if (j > 0) {
             LaunchCold<C>::double_n(ctx->stream, sc.sw[cur], cnt, ctx->c * ctx->F, sc.tmp);
-            LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[cur ^ 1]);
+            LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[cur ^ 1], infmask, ctx->bad);
             cur ^= 1;
         }
-        LaunchCold<C>::make_entries(ctx->stream, sc.sw[cur], cnt, ctx->tables + ((size_t)j * ctx->n + first) * eb, ctx->acc_mix == 0);
+        LaunchCold<C>::make_entries(ctx->stream, sc.sw[cur], cnt, ctx->tables + ((size_t)j * ctx->n + first) * eb, ctx->acc_mix == 0, infmask, ctx->bad);
     }
     if (cur != 0) { affine_t *t = sc.sw[0]; sc.sw[0] = sc.sw[1]; sc.sw[1] = t; }
 }
@@ -319,8 +338,8 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
     for (uint32_t first = 0; first < gen_n; first += chunk) {
         uint32_t cnt = gen_n - first < chunk ? gen_n - first : chunk;
         LaunchCold<C>::gen_points(ctx->stream, first, cnt, seed, mode, (uint32_t)(distinct ? distinct : 1), gx, gy, sc.tmp);
-        LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[0]);
-        emit_tables<C>(ctx, sc, first, cnt);
+        LaunchCold<C>::batch_normalize(ctx->stream, sc.tmp, cnt, sc.sw[0], nullptr, nullptr);
+        emit_tables<C>(ctx, sc, first, cnt, nullptr);
     }
     if (gen_n < n) {        // the replicas of a point have the same entry in every table
         const uint32_t vec = (uint32_t)(ctx->entry_bytes / 16);
@@ -335,6 +354,22 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
     return 0;
 }
 
+// Bases the bucket coordinate system cannot represent (twisted Edwards on BLS12-377: points with y = 0 or s (x + 1) = -1,
+// which lie outside the prime-order subgroup) were counted while the entries were built: refuse them loudly.  The XYZZ
+// arithmetic (b200msm_set_bucket_arithmetic) takes every on-curve point, as arkworks does
+// (P1B/nickray/driver/algebra/ec/src/models/short_weierstrass_jacobian.rs:662-729).
+static int check_bad_entries(b200msm_ctx *ctx) {
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (bad == 0) return 0;
+    CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
+    ctx->n = 0;                          // the tables are unusable: a later MSM call fails with "bases not set"
+    ctx->plan_ok = false;
+    return ctx->fail(-3, std::to_string(bad) + " table entries belong to bases outside the prime-order subgroup with no twisted-Edwards image; "
+                         "select the XYZZ bucket arithmetic (b200msm_set_bucket_arithmetic(ctx, 1) or B200MSM_GROUP=xyzz)");
+}
+
 template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride) {
     const uint64_t chunk = 1ull << 22;
     table_scratch_t sc;
@@ -346,11 +381,11 @@ template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_h
         uint64_t cnt = n - first < chunk ? n - first : chunk;
         rc = h2d(ctx, raw, (const uint8_t *)affine_host + first * stride, (size_t)(cnt * stride), ctx->stream); if (rc) return rc;
         LaunchCold<C>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, sc.sw[0], ctx->infmask + first / 32);
-        emit_tables<C>(ctx, sc, (uint32_t)first, (uint32_t)cnt);
+        emit_tables<C>(ctx, sc, (uint32_t)first, (uint32_t)cnt, ctx->infmask + first / 32);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    return 0;
+    return check_bad_entries(ctx);
 }
 
 // generator in the device representation (P1B/nickray/driver/bls12-377/src/curves/g1.rs:159-165)
@@ -395,9 +430,11 @@ template <class C> static int run_chunk_t(b200msm_ctx *ctx, const void *scalars_
     uint32_t *piece_off = ctx->piece_off + (size_t)chunk * (nb + 1);
     xyzz_t *res = ctx->res + (size_t)chunk * ctx->max_pieces;
     int launches = 0;
-    if (chunk == 0) {
-        ctx->ev = ctx->evr[ctx->ev_steps % b200msm_ctx::EV_RING];
-        ctx->ev_steps++;
+    {
+        const int slot = (int)(ctx->ev_sets % b200msm_ctx::EV_RING);
+        ctx->ev = ctx->evr[slot];
+        ctx->ev_last[slot] = 4;
+        ctx->ev_sets++;
         cudaEventRecord(ctx->ev[0], st);
     }
     CK(cudaMemsetAsync(ctx->counts, 0, ((size_t)nb + 1) * 4, st));
@@ -452,15 +489,21 @@ template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *
     LaunchCold<C>::finalize(st, ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac);
     launches++;
     cudaEventRecord(ctx->ev[6], st);
+    ctx->ev_last[(ctx->ev_sets - 1) % b200msm_ctx::EV_RING] = 6;
+    ctx->ev_steps++;
     ctx->launches += launches;
     CK(cudaGetLastError());
     return 0;
 }
 static int run_chunk(b200msm_ctx *ctx, const void *scalars_dev, uint32_t first, uint32_t count, int chunk) {
-    return ctx->curve == 0 ? run_chunk_t<Bls12_377>(ctx, scalars_dev, first, count, chunk) : run_chunk_t<Bls12_381>(ctx, scalars_dev, first, count, chunk);
+    int rc = 0;
+    BY_GROUP(ctx->kind, rc = run_chunk_t<C>(ctx, scalars_dev, first, count, chunk));
+    return rc;
 }
 static int run_reduce(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz) {
-    return ctx->curve == 0 ? run_reduce_t<Bls12_377>(ctx, nchunks, out_jac, out_xyzz) : run_reduce_t<Bls12_381>(ctx, nchunks, out_jac, out_xyzz);
+    int rc = 0;
+    BY_GROUP(ctx->kind, rc = run_reduce_t<C>(ctx, nchunks, out_jac, out_xyzz));
+    return rc;
 }
 // one MSM on the context's stream.  scalars: device, n x 32 bytes.  Exactly one of out_jac / out_xyzz is set.
 static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz) {
@@ -510,7 +553,9 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     ctx->curve = curve; ctx->device = device; ctx->req_c = window_bits; ctx->req_tables = tables;
     if (const char *e = getenv("B200MSM_ACC")) ctx->acc_mix = strcmp(e, "fp64") == 0 ? 0 : 8;
     if (const char *e = getenv("B200MSM_HOST_CHUNKS")) ctx->host_chunks = atoi(e);
-    ctx->entry_bytes = curve == 0 ? LaunchCold<Bls12_377>::entry_bytes() : LaunchCold<Bls12_381>::entry_bytes();
+    if (const char *g = getenv("B200MSM_GROUP")) if (curve == 0 && strcmp(g, "xyzz") == 0) ctx->kind = 2;
+    if (curve == 1) ctx->kind = 1;
+    BY_GROUP(ctx->kind, ctx->entry_bytes = LaunchCold<C>::entry_bytes());
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -565,11 +610,24 @@ int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream) {
     return 0;
 }
 
+int b200msm_set_bucket_arithmetic(b200msm_ctx *ctx, int arithmetic) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (arithmetic != 0 && arithmetic != 1) return ctx->fail(-1, "b200msm_set_bucket_arithmetic: 0 = the curve's default, 1 = XYZZ");
+    const int kind = ctx->curve == 1 ? 1 : (arithmetic == 1 ? 2 : 0);
+    if (kind == ctx->kind) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->free_plan();                     // entry size and tables change: bases must be set again
+    ctx->kind = kind;
+    BY_GROUP(ctx->kind, ctx->entry_bytes = LaunchCold<C>::entry_bytes());
+    return 0;
+}
+
 int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!affine_host || n == 0 || n >= (1ull << 31) || stride < 96 || (stride & 7)) return ctx->fail(-1, "b200msm_set_bases: bad argument");
     rc = alloc_plan(ctx, n); if (rc) return rc;
-    return ctx->curve == 0 ? set_bases_t<Bls12_377>(ctx, affine_host, n, stride) : set_bases_t<Bls12_381>(ctx, affine_host, n, stride);
+    BY_GROUP(ctx->kind, rc = set_bases_t<C>(ctx, affine_host, n, stride));
+    return rc;
 }
 
 int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int mode, uint64_t distinct) {
@@ -579,7 +637,8 @@ int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int
     rc = alloc_plan(ctx, n); if (rc) return rc;
     fp gx, gy;
     generator(ctx->curve, gx, gy);
-    return ctx->curve == 0 ? gen_bases_t<Bls12_377>(ctx, seed, mode, distinct, gx, gy) : gen_bases_t<Bls12_381>(ctx, seed, mode, distinct, gx, gy);
+    BY_GROUP(ctx->kind, rc = gen_bases_t<C>(ctx, seed, mode, distinct, gx, gy));
+    return rc;
 }
 
 int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uint64_t n) {
@@ -588,8 +647,7 @@ int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uin
     CK(cudaStreamSynchronize(ctx->stream));
     uint32_t *tmp = nullptr;
     CK(cudaMalloc((void **)&tmp, (size_t)n * 96));
-    if (ctx->curve == 0) LaunchCold<Bls12_377>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp, ctx->acc_mix == 0);
-    else LaunchCold<Bls12_381>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp, ctx->acc_mix == 0);
+    BY_GROUP(ctx->kind, LaunchCold<C>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp, ctx->acc_mix == 0));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(affine96_host, tmp, (size_t)n * 96, cudaMemcpyDeviceToHost));
     cudaFree(tmp);
@@ -620,8 +678,7 @@ int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64
 int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!xyzz_dev || count < 1 || !out_jacobian_dev) return ctx->fail(-1, "b200msm_combine_device: bad argument");
-    if (ctx->curve == 0) LaunchCold<Bls12_377>::combine(ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev);
-    else LaunchCold<Bls12_381>::combine(ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev);
+    BY_GROUP(ctx->kind, LaunchCold<C>::combine(ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev));
     CK(cudaGetLastError());
     return 0;
 }
@@ -712,8 +769,10 @@ int b200msm_plan_info(int curve, uint64_t n, uint64_t free_bytes, int window_bit
         tables < 0 || chunks < 1 || chunks > 8) return -1;
     b200msm_ctx tmp;
     tmp.curve = curve; tmp.req_c = window_bits; tmp.req_tables = tables; tmp.plan_chunks = chunks;
-    tmp.entry_bytes = curve == 0 ? LaunchCold<Bls12_377>::entry_bytes() : LaunchCold<Bls12_381>::entry_bytes();
-    choose_plan(&tmp, n, (size_t)free_bytes);
+    tmp.kind = curve;
+    if (const char *g = getenv("B200MSM_GROUP")) if (curve == 0 && strcmp(g, "xyzz") == 0) tmp.kind = 2;
+    BY_GROUP(tmp.kind, tmp.entry_bytes = LaunchCold<C>::entry_bytes());
+    if (!choose_plan(&tmp, n, (size_t)free_bytes)) return -1;
     info[0] = n; info[1] = tmp.c; info[2] = tmp.W; info[3] = tmp.T; info[4] = tmp.F; info[5] = tmp.nbuckets;
     info[6] = (uint64_t)tmp.T * n * tmp.entry_bytes;      // bytes of base tables
     info[7] = (uint64_t)tmp.W * n;                        // point references per MSM
@@ -726,33 +785,48 @@ int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]) {
     return 0;
 }
 
+// Sums the stage times of the newest `want` complete MSMs still in the ring (every chunk's set counted): walks the sets from
+// the newest back; a set with ev_last == 6 closes an MSM, the sets before it down to the previous closing set are its chunks.
+static int stage_sums(b200msm_ctx *ctx, uint64_t want, float sum[6], uint64_t *covered) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 6; i++) sum[i] = 0.f;
+    *covered = 0;
+    const uint64_t have = ctx->ev_sets < (uint64_t)b200msm_ctx::EV_RING ? ctx->ev_sets : (uint64_t)b200msm_ctx::EV_RING;
+    float pend[6] = {};
+    bool open = false;                    // pend holds the sets of an MSM whose first chunk has not been reached yet
+    for (uint64_t k = 0; k < have && *covered < want; k++) {
+        const int slot = (int)((ctx->ev_sets - 1 - k) % b200msm_ctx::EV_RING);
+        const int last = ctx->ev_last[slot];
+        if (last == 6) {                  // a closing set: whatever was pending is complete
+            if (open) { for (int i = 0; i < 6; i++) sum[i] += pend[i]; (*covered)++; if (*covered == want) break; }
+            for (int i = 0; i < 6; i++) pend[i] = 0.f;
+            open = true;
+        } else if (!open) continue;       // chunks of an MSM that has not been reduced yet
+        for (int i = 0; i < last; i++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ctx->evr[slot][i], ctx->evr[slot][i + 1])); pend[i] += ms; }
+    }
+    if (open && *covered < want && ctx->ev_sets <= (uint64_t)b200msm_ctx::EV_RING) { for (int i = 0; i < 6; i++) sum[i] += pend[i]; (*covered)++; }
+    return 0;
+}
+
 int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!stage_ms) return -1;
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < 6; i++) CK(cudaEventElapsedTime(&stage_ms[i], ctx->ev[i], ctx->ev[i + 1]));
-    return 0;
+    uint64_t covered = 0;
+    return stage_sums(ctx, 1, stage_ms, &covered);
 }
 
 int b200msm_reset_stage_stats(b200msm_ctx *ctx) {
     int rc = check_ctx(ctx); if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ev_steps = 0;
+    ctx->ev_sets = 0;
     return 0;
 }
 
 int b200msm_get_stage_ms_sum(b200msm_ctx *ctx, float stage_ms_sum[6], uint64_t *steps) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!stage_ms_sum || !steps) return -1;
-    CK(cudaStreamSynchronize(ctx->stream));
-    uint64_t cnt = ctx->ev_steps < (uint64_t)b200msm_ctx::EV_RING ? ctx->ev_steps : (uint64_t)b200msm_ctx::EV_RING;
-    for (int i = 0; i < 6; i++) stage_ms_sum[i] = 0.f;
-    for (uint64_t k = 0; k < cnt; k++) {
-        cudaEvent_t *ev = ctx->evr[(ctx->ev_steps - 1 - k) % b200msm_ctx::EV_RING];
-        for (int i = 0; i < 6; i++) { float ms = 0.f; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); stage_ms_sum[i] += ms; }
-    }
-    *steps = cnt;
-    return 0;
+    return stage_sums(ctx, ctx->ev_steps, stage_ms_sum, steps);
 }
 
 // ---- one-call form: arkworks VariableBaseMSM::multi_scalar_mul(bases, scalars) ---------------------------------
@@ -825,7 +899,7 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
             CK(cudaEventRecord(ctx->ev_raw_copied[b], ctx->copy_stream));
             CK(cudaStreamWaitEvent(cs, ctx->ev_raw_copied[b], 0));
             LaunchCold<C>::convert_points(cs, ctx->raw_buf[b], (uint32_t)cnt, (uint32_t)stride, ctx->sw_buf, ctx->infmask + s / 32);
-            LaunchCold<C>::make_entries(cs, ctx->sw_buf, (uint32_t)cnt, ctx->tables + s * ctx->entry_bytes, ctx->acc_mix == 0);
+            LaunchCold<C>::make_entries(cs, ctx->sw_buf, (uint32_t)cnt, ctx->tables + s * ctx->entry_bytes, ctx->acc_mix == 0, ctx->infmask + s / 32, ctx->bad);
             CK(cudaEventRecord(ctx->ev_raw_free[b], cs));
         }
         if (conv_async) { CK(cudaEventRecord(ctx->ev_conv, cs)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_conv, 0)); }
@@ -839,15 +913,22 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
     rc = run_reduce(ctx, used, ctx->out_dev, nullptr);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_host, ctx->out_dev, 144, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, ctx->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     const double issue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
     CK(cudaStreamSynchronize(ctx->stream));
     if (getenv("B200MSM_TRACE")) {
         float st[6] = {};
-        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&st[i], ctx->ev[i], ctx->ev[i + 1]);      // last chunk's stages + the reduction
+        uint64_t cov = 0;
+        stage_sums(ctx, 1, st, &cov);                                                               // summed over the call's chunks
         fprintf(stderr, "b200msm one-call n=%llu c=%d W=%d F=%d chunks=%d: total %.1f ms, issued after %.1f ms, in h2d %.1f ms (waiting for a slot %.1f ms); "
-                "last chunk: digits %.1f scatter %.1f pieces %.1f accumulate %.1f, reduce %.1f finalize %.1f ms\n", (unsigned long long)n, ctx->c, ctx->W, ctx->F, nch,
+                "all chunks: digits %.1f scatter %.1f pieces %.1f accumulate %.1f, reduce %.1f finalize %.1f ms\n", (unsigned long long)n, ctx->c, ctx->W, ctx->F, nch,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(), issue_ms, ctx->h2d_ms, ctx->h2d_wait_ms,
                 st[0], st[1], st[2], st[3], st[4], st[5]);
+    }
+    if (bad) {
+        CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
+        return ctx->fail(-3, std::to_string(bad) + " bases lie outside the prime-order subgroup and have no twisted-Edwards image; set B200MSM_GROUP=xyzz");
     }
     return 0;
 }
@@ -876,8 +957,7 @@ int b200msm_variable_base_msm(int curve, int device, const void *affine_host, ui
     int rc = check_ctx(ctx);
     ctx->plan_chunks = one_call_chunks(ctx, n);       // the window plan knows the reduction sums over this many chunks
     if (rc == 0) rc = alloc_plan(ctx, n);
-    if (rc == 0) rc = curve == 0 ? one_call_t<Bls12_377>(ctx, (const uint8_t *)affine_host, n, stride, (const uint8_t *)scalars_host, out_jacobian_host)
-                                 : one_call_t<Bls12_381>(ctx, (const uint8_t *)affine_host, n, stride, (const uint8_t *)scalars_host, out_jacobian_host);
+    if (rc == 0) BY_GROUP(ctx->kind, rc = one_call_t<C>(ctx, (const uint8_t *)affine_host, n, stride, (const uint8_t *)scalars_host, out_jacobian_host));
     if (rc) {                                         // keep the message, drop the context: the next call starts clean
         g_create_error = ctx->err;
         b200msm_destroy(ctx);
@@ -930,12 +1010,11 @@ int b200msm_test_ec_op(int curve, int op, void *acc, const void *other, uint64_t
 }
 
 int b200msm_test_grp_op(int curve, int op, const void *a96, const void *b96, void *out104, uint64_t n, int reps) {
-    if (!a96 || !b96 || !out104 || n == 0 || (curve != 0 && curve != 1) || op < 0 || op > 3 || reps < 0) return -1;
+    if (!a96 || !b96 || !out104 || n == 0 || curve < 0 || curve > 2 || op < 0 || op > 3 || reps < 0) return -1;      // 2: BLS12-377 in XYZZ
     affine_abi_t *da, *db; uint32_t *dout;
     TCK(cudaMalloc((void **)&da, (size_t)n * 96)); TCK(cudaMalloc((void **)&db, (size_t)n * 96)); TCK(cudaMalloc((void **)&dout, (size_t)n * 104));
     TCK(cudaMemcpy(da, a96, (size_t)n * 96, cudaMemcpyHostToDevice)); TCK(cudaMemcpy(db, b96, (size_t)n * 96, cudaMemcpyHostToDevice));
-    if (curve == 0) LaunchCold<Bls12_377>::test_grp(op, da, db, dout, (uint32_t)n, reps);
-    else LaunchCold<Bls12_381>::test_grp(op, da, db, dout, (uint32_t)n, reps);
+    BY_GROUP(curve, LaunchCold<C>::test_grp(op, da, db, dout, (uint32_t)n, reps));
     TCK(cudaGetLastError());
     TCK(cudaMemcpy(out104, dout, (size_t)n * 104, cudaMemcpyDeviceToHost));
     cudaFree(da); cudaFree(db); cudaFree(dout);

@@ -70,6 +70,35 @@ template <class C> struct Te {
     }
 
     // acc += q   (add-2008-hwcd-3 with Z2 = 1 and k T2 precomputed: 7 M)
+#if defined(TE_LAZY_NORM)
+    // The same with the carry propagation left out wherever the multiplier's 64-bit columns allow it.  Notation: L = bound
+    // of limbs 0..12 in units of 2^28 (the top limb is bounded by the value and stays below 2^17), V = value in units of p.
+    // Stored coordinates and entry values are multiplier outputs or canonical: L 1, V 2.  Karatsuba (Fp::mul_karatsuba)
+    // with operands of limb bounds La, Lb: half sums 2 La, 2 Lb; a middle column holds 7 products: 28 La Lb 2^56; the
+    // z0 / z2 columns 7 La Lb; after z1 is folded in a column is below (28 + 7) La Lb 2^56, the reduction adds 14 more
+    // products m p_j < 2^56 and a carry < 2^36:  (35 La Lb + 15) 2^56 < 2^64  <=>  La Lb <= 6.
+    FP_HD static void madd(xyzz_t &acc, const te_pre_t &q) {
+        fp a, b, c, d, e, f, g, h;
+        F::template sub_raw<3>(a, acc.y, acc.x);  // Y1 - X1            L 3     V 5
+        E::M(a, a, q.ymx);                        // A          3 x 1   L 1     V 2
+        F::add_raw(b, acc.y, acc.x);              // Y1 + X1            L 2     V 4
+        E::M(b, b, q.ypx);                        // B          2 x 1
+        E::M(c, acc.zzz, q.kt);                   // C          1 x 1
+        F::add_raw(d, acc.zz, acc.zz);            // D = 2 Z1           L 2     V 4
+        F::template sub_raw<3>(e, b, a);          // E = B - A          L 3     V 5
+        F::template sub<3>(f, d, c);              // F = D - C          L 1     V 7     (normalised: it meets E and G)
+        F::add_raw(g, d, c);                      // G = D + C          L 3     V 6
+#if TE_LAZY_NORM >= 2
+        F::add_raw(h, b, a);                      // H = B + A          L 2     V 4     (3 x 2 = 6: the largest admissible pair)
+#else
+        F::add(h, b, a);                          // H = B + A          L 1     V 4     (normalised: it meets E and G)
+#endif
+        E::M(acc.x, e, f);                        // X3 = E F   3 x 1
+        E::M(acc.y, g, h);                        // Y3 = G H   3 x 1 (3 x 2)
+        E::M(acc.zzz, e, h);                      // T3 = E H   3 x 1 (3 x 2)
+        E::M(acc.zz, f, g);                       // Z3 = F G   1 x 3
+    }
+#else
     FP_HD static void madd(xyzz_t &acc, const te_pre_t &q) {
         fp a, b, c, d, e, f, g, h;
         F::template sub<3>(a, acc.y, acc.x);      // Y1 - X1                    5
@@ -87,6 +116,7 @@ template <class C> struct Te {
         E::M(acc.zzz, e, h);                      // T3 = E H
         E::M(acc.zz, f, g);                       // Z3 = F G
     }
+#endif
     // a += b, both extended (add-2008-hwcd-3: 9 M); also doubles (b may equal a)
     FP_HD static void add(xyzz_t &a, const xyzz_t &b) {
         fp A, B, Cc, D, e, f, g, h, t, k;

@@ -17,8 +17,8 @@
  *   G1Projective  144 bytes: Jacobian x, y, z (x/z^2, y/z^3); this library returns (x_affine, y_affine, 1) or the
  *                            arkworks zero (1, 1, 0) -- any representative is valid, the harness compares projectively
  *
- * All functions return 0 on success; -1 = bad argument, -2 = CUDA extension unusable (no device), any positive value
- * is a cudaError_t.  After a failure b200msm_last_error() describes it.  A context is used from one thread at a
+ * All functions return 0 on success; -1 = bad argument, -2 = CUDA extension unusable (no device), -3 = bases the
+ * selected bucket arithmetic cannot represent (b200msm_set_bucket_arithmetic), any positive value is a cudaError_t.  After a failure b200msm_last_error() describes it.  A context is used from one thread at a
  * time (the harness calls multi_scalar_mult repeatedly on the same context from one thread).
  */
 #ifndef B200MSM_H
@@ -44,8 +44,21 @@ const char *b200msm_last_error(const b200msm_ctx *ctx);   /* ctx may be NULL: er
 /* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*); NULL = own stream. */
 int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream);
 
-/* multi_scalar_mult_init: upload `n` arkworks G1Affine records (stride bytes apart, 96 <= stride; the infinity
- * flag is read only when stride > 96) and build the base tables 2^(c*F*j) * P_i.  Replaces
+/* Bucket arithmetic of the context; call before the bases are set (it drops tables already built).
+ *   0  the curve's default: twisted-Edwards extended coordinates on BLS12-377 (7 M unified mixed add), XYZZ on BLS12-381.
+ *      The twisted-Edwards model represents every point of G1 and every generic on-curve point; the few on-curve points
+ *      WITHOUT an image (y = 0, or s (x + 1) = -1: all outside the prime-order subgroup) make b200msm_set_bases fail with
+ *      -3 instead of producing a wrong sum.  Not detected: two bases outside G1 whose difference is one of the model's
+ *      exceptional low-order points meeting in one bucket -- impossible for bases in G1, the harness contract.
+ *   1  XYZZ (8 M + 2 S mixed add): complete on every on-curve point, the contract of arkworks' add_assign_mixed
+ *      (P1B/nickray/driver/algebra/ec/src/models/short_weierstrass_jacobian.rs:662-729).  About 1.35x slower.
+ * The environment variable B200MSM_GROUP=xyzz selects 1 for every BLS12-377 context the process creates (Families A, B
+ * and the one-call form, which have no such argument). */
+int b200msm_set_bucket_arithmetic(b200msm_ctx *ctx, int arithmetic);
+
+/* multi_scalar_mult_init: upload `n` arkworks G1Affine records (stride bytes apart, 96 <= stride; a base is at infinity
+ * when its flag byte at offset 96 is set (stride > 96) or when x = y = 0, the encoding of the flag-less 96-byte
+ * blst_p1_affine records, sppark ec/xyzz_t.hpp:44-45) and build the base tables 2^(c*F*j) * P_i.  Replaces
  * mult_pippenger_init / MSMPreprocessPoints + precomputePointsKernel (P1A/yrrid/yrrid-msm/PrecomputePoints.cu:10-39). */
 int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride);
 

@@ -20,16 +20,43 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = os.environ.get("REF_ROOT", "/root/reference") + "/open-division/prize1-msm/prize1a-msm-gpu/combined-top-solutions/combined-msm/MSM.cu"
+P1A = os.environ.get("REF_ROOT", "/root/reference") + "/open-division/prize1-msm/prize1a-msm-gpu"
+ENTRIES = {"combined": (P1A + "/combined-top-solutions/combined-msm/MSM.cu", "libcombined_msm"),      # the fastest entry (default)
+           "yrrid": (P1A + "/yrrid/yrrid-msm/MSM.cu", "libyrrid_msm")}                                 # its parent: same driver, yrrid's own field code
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 
+def patch_ptx(path):
+    """--volatile=planning: in every function of the PTX except the two arithmetic kernels (computeBucketSums, reduceBuckets) and
+    the table precompute, make ALL shared-memory loads and stores volatile, so the assembler keeps the program order the
+    entry's hand-written inter-warp protocols (byte stores polled by another warp, Partition1024.cu:124-147, 223-240) rely on."""
+    out, keep, n = [], False, 0
+    for line in open(path):
+        m = re.match(r"\s*(?:\.visible\s+|\.weak\s+)?\.(entry|func)\s+(?:\([^)]*\)\s*)?(\w+)", line)
+        if m:
+            keep = any(k in m.group(2) for k in ("computeBucketSums", "reduceBuckets", "precomputePoints"))
+        if not keep:
+            new = re.sub(r"\b(ld|st)\.shared\.", r"\1.volatile.shared.", line)
+            n += new != line
+            line = new
+        out.append(line)
+    open(path, "w").writelines(out)
+    print(f"patched {n} shared loads / stores outside the arithmetic kernels")
+
+
 def main():
+    if "--patch-ptx" in sys.argv:
+        return patch_ptx(sys.argv[sys.argv.index("--patch-ptx") + 1])
     plain = "--plain" in sys.argv
+    wide = "--volatile=planning" in sys.argv     # every shared load AND store of the planning kernels volatile (not only the u32 loads)
+    diag = "--diag" in sys.argv                  # build oracle/ref_entry_diag.cu (includes the entry's MSM.cu) instead: adds MSMDiagOneBatch
+    entry = "yrrid" if "--entry=yrrid" in sys.argv else "combined"
+    REF, stem = ENTRIES[entry]
     out_dir = os.path.join(HERE, "_ref")
     os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "libcombined_msm_plain.so" if plain else "libcombined_msm.so")
-    cmd = [NVCC, "-O3", "-gencode", "arch=compute_100,code=sm_100", "-w", "-shared", "-Xcompiler", "-fPIC", "-o", out, REF]
+    out = os.path.join(out_dir, stem + ("_plain" if plain else "") + ("_v2" if wide else "") + ("_diag" if diag else "") + ".so")
+    src = [os.path.join(HERE, "ref_entry_diag.cu"), "-I", os.path.dirname(REF)] if diag else [REF]
+    cmd = [NVCC, "-O3", "-gencode", "arch=compute_100,code=sm_100", "-w", "-shared", "-Xcompiler", "-fPIC", "-o", out] + src
     dry = subprocess.run(cmd + ["-dryrun"], capture_output=True, text=True, check=True).stderr
     steps = [l[3:] for l in dry.splitlines() if l.startswith("#$ ")]
     script, patched = ["set -e"], 0
@@ -46,12 +73,15 @@ def main():
             m = re.search(r'-o "([^"]+\.ptx)"', s)
             if not m:
                 raise SystemExit("could not find the PTX output of the compiler step")
-            script.append(f"sed -i 's/ld\\.shared\\.u32/ld.volatile.shared.u32/g' \"{m.group(1)}\"")
-            script.append(f"echo patched $(grep -c 'ld.volatile.shared.u32' \"{m.group(1)}\") scalar shared loads")
+            if wide:
+                script.append(f"python3 {os.path.join(HERE, 'build_ref_entry.py')} --patch-ptx \"{m.group(1)}\"")
+            else:
+                script.append(f"sed -i 's/ld\\.shared\\.u32/ld.volatile.shared.u32/g' \"{m.group(1)}\"")
+                script.append(f"echo patched $(grep -c 'ld.volatile.shared.u32' \"{m.group(1)}\") scalar shared loads")
             patched += 1
     if not plain and patched != 1:
         raise SystemExit(f"expected one compiler step, found {patched}")
-    steps_file = os.path.join(out_dir, "build_steps.sh")
+    steps_file = os.path.join(out_dir, f"build_steps_{entry}{'_v2' if wide else ''}{'_diag' if diag else ''}.sh")
     with open(steps_file, "w") as f:
         f.write("\n".join(script) + "\n")
     rc = subprocess.run(["bash", steps_file]).returncode

@@ -110,7 +110,20 @@ static void te_ops(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_
 template <class C> static void te_constants(uint32_t *out) {
     for (int i = 0; i < FP_LIMBS; i++) { out[i] = C::te_k(i); out[14 + i] = C::te_f(i); out[28 + i] = C::te_s(i); out[42 + i] = C::te_s3(i); out[56 + i] = C::te_cy(i); }
 }
+// the multiplier on raw limb arrays (14 x u32 each): operands with limbs above 2^28 (the un-normalised sums Te::madd feeds it)
+template <class C> static void fp_mul_raw(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fp x, y, t;
+        for (int j = 0; j < FP_LIMBS; j++) { x.l[j] = a[i * FP_LIMBS + j]; y.l[j] = b[i * FP_LIMBS + j]; }
+        Fp<C>::mul(t, x, y);
+        for (int j = 0; j < FP_LIMBS; j++) r[i * FP_LIMBS + j] = t.l[j];
+    }
+}
 extern "C" {
+int emul_fp_mul_raw(int curve, const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) {
+    if (curve == 0) fp_mul_raw<Bls12_377>(a, b, r, n); else fp_mul_raw<Bls12_381>(a, b, r, n);
+    return 0;
+}
 int emul_te_op(int op, const void *a, const void *b, void *out, size_t n, int reps) { te_ops(op, (const affine_abi_t *)a, (const affine_abi_t *)b, (uint32_t *)out, n, reps); return 0; }
 int emul_te_constants(uint32_t *out) { te_constants<Bls12_377>(out); return 0; }
 int emul_fp_op(int curve, int op, const void *a, const void *b, void *r, size_t n) {

@@ -141,3 +141,14 @@ def test_window_plan_invariants_and_headline_choice(M):
     assert (p["window_bits"], p["tables"], p["folded_windows"]) == (23, 3, 4)
     with pytest.raises(M.MsmError):
         M.plan_info(0)
+
+
+def test_window_plan_rejects_combinations_beyond_the_bucket_limit(M):
+    """A forced window of 25 / 26 bits with too few tables needs more than 2^27 buckets: an error, not a division by zero
+    (choose_plan returned c = 0 and the process died with SIGFPE before)."""
+    for wb in (25, 26):
+        with pytest.raises(M.MsmError):
+            M.plan_info(1 << 20, 0, 170 << 30, wb, 1)
+    p = M.plan_info(1 << 20, 0, 170 << 30, 26, 0)           # all tables: one folded window of 2^25 buckets
+    assert p["buckets"] == 1 << 25 and p["folded_windows"] == 1
+    assert "b200msm_set_bucket_arithmetic" in M.EXPORTED_SYMBOLS

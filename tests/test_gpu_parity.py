@@ -559,3 +559,204 @@ def test_bls12_381_reference_points_through_the_engine(M, oracle, bls381_small_m
     eng.close()
     assert np.array_equal(got, KA.expected_affine(O, 1, t))
     assert np.array_equal(got, O.jac_to_affine(O.ark_msm(pts, sc, 1), 1)[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Round 2: BASELINE configs 3 and 5 at their full sizes, the folded-window plans at scale, bases outside G1
+def _closed_form_check(M, O, curve, n, window_bits=0, tables=0, chunk_rows=1 << 24, expect_plan=None):
+    """Bases k_i G generated on the device, uniform scalars, result == (sum s_i k_i mod r) G.  The scalars come back to the
+    host in chunks of chunk_rows (2^28 scalars are 8.6 GB)."""
+    import gc
+    import torch
+    import known_answer as KA
+    gc.collect()
+    torch.cuda.empty_cache()
+    eng = M.Engine(curve, window_bits=window_bits, tables=tables)
+    eng.set_bases_generated(n, seed=77, mode=0, distinct=1 << 15)
+    info = eng.info()
+    if expect_plan:
+        for k, v in expect_plan.items():
+            assert info[k] == v, (k, info)
+    sc = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    eng.generate_scalars(sc.data_ptr(), n, 5)
+    out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    eng.msm_device(sc.data_ptr(), n, out.data_ptr())
+    eng.sync()
+    r = O.constants(curve)["r"]
+    t = 0
+    for a0 in range(0, n, chunk_rows):
+        rows = min(chunk_rows, n - a0)
+        part = sc[a0 * 32:(a0 + rows) * 32].cpu().numpy().reshape(rows, 32)
+        i = np.arange(a0, a0 + rows, dtype=np.uint64)
+        logs = KA.splitmix64(np.uint64(77) + (i % np.uint64(1 << 15))) | np.uint64(1)
+        t = (t + KA.dot_mod_r(part, logs, r)) % r
+    got = O.jac_to_affine(out.cpu().numpy(), curve)[0]
+    eng.close()
+    del sc, out
+    torch.cuda.empty_cache()
+    assert np.array_equal(got, KA.expected_affine(O, curve, t)), info
+    return info
+
+
+def test_bls12_381_2pow24_closed_form(M, oracle):
+    """BASELINE config 5 at its size: BLS12-381 G1, 2^24 points (XYZZ buckets, 255-bit scalars)."""
+    info = _closed_form_check(M, oracle, 1, 1 << 24)
+    assert info["folded_windows"] == 1
+
+
+def test_bls12_377_2pow22_three_tables_two_level_scatter(M, oracle, monkeypatch):
+    """The plan 2^28 runs on one GPU -- 3 tables, 4 folded windows -- at a size where the two-level scatter's bins are real
+    (8 bins of 24 MB of list), forced by B200MSM_BIN_MIN_MB."""
+    monkeypatch.setenv("B200MSM_BIN_MIN_MB", "0")
+    info = _closed_form_check(M, oracle, 0, 1 << 22, window_bits=23, tables=3, expect_plan={"tables": 3, "folded_windows": 4, "windows": 11})
+    assert info["buckets"] == 4 << 22
+
+
+def test_bls12_377_2pow28_closed_form(M, oracle):
+    """BASELINE config 3's largest size: 2^28 points on one B200.  38.7 GB per table leaves room for 3 tables, so the 11
+    windows fold to 4 (16.8 M buckets) -- the only size at which that plan is the automatic choice."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 168 << 30:
+        pytest.skip(f"needs ~168 GB of free device memory, {free >> 30} GB available")
+    info = _closed_form_check(M, oracle, 0, 1 << 28)
+    assert info["folded_windows"] > 1 and info["tables"] < info["windows"], info
+
+
+def _random_curve_points(O, n, seed, curve=0):
+    """n random points of the CURVE y^2 = x^3 + b, not of G1: x uniform, y = sqrt(x^3 + b) where it exists (no cofactor
+    clearing).  Their order is a multiple of a large prime other than r with probability ~1."""
+    rng = np.random.default_rng(seed)
+    p = O.constants(curve)["p"]
+    out = np.zeros((n, 104), np.uint8)
+    k = 0
+    while k < n:
+        x = int.from_bytes(rng.bytes(48), "little") % p
+        comp = np.frombuffer(x.to_bytes(48, "little"), np.uint8).copy()
+        if rng.integers(0, 2):
+            comp[47] |= 0x80
+        one = np.zeros(104, np.uint8)
+        if O.lib().oracle_decompress(curve, comp.ctypes.data, 1, one.ctypes.data) == 0:
+            out[k] = one
+            k += 1
+    return out
+
+
+def test_bases_outside_the_prime_order_subgroup(M, oracle):
+    """arkworks' add_assign_mixed is correct for EVERY on-curve point (short_weierstrass_jacobian.rs:662-729), G1 or not.
+    Pinned behaviour of this library: (1) generic on-curve points outside G1 give the oracle's sum in both bucket
+    arithmetics; (2) a base without a twisted-Edwards image (the 2-torsion point (-1, 0)) is REFUSED by the default
+    arithmetic (error -3), never summed wrongly; (3) the XYZZ arithmetic takes it, tables > 1 included (2^k P = infinity)."""
+    O = oracle
+    n = 1500
+    pts = _random_curve_points(O, n, seed=321)
+    assert O.on_curve(pts)
+    r = O.constants(0)["r"]
+    rG = O.naive_msm(pts[:1], np.frombuffer(int(r).to_bytes(32, "little"), np.uint8).reshape(1, 32))
+    assert O.jac_to_affine(rG)[0, 96] == 0, "r * P should not be the identity: P must lie outside G1"
+    sc = O.gen_scalars(n, seed=322)
+    want = O.jac_to_affine(O.ark_msm(pts, sc))
+    for xyzz in (False, True):
+        for tables in (0, 1):
+            e = M.Engine(0, tables=tables)
+            e.set_bucket_arithmetic(xyzz)
+            e.set_bases(pts)
+            assert np.array_equal(O.jac_to_affine(e.msm_host(sc)), want), (xyzz, tables)
+            e.close()
+    # the point of order 2: x = -1, y = 0
+    p = O.constants(0)["p"]
+    t2 = np.zeros((1, 104), np.uint8)
+    canon = np.frombuffer((p - 1).to_bytes(48, "little") + (0).to_bytes(48, "little"), np.uint8)
+    t2[0, :96] = O.fp_convert(canon, True).reshape(-1)
+    assert O.on_curve(t2)
+    bad = pts.copy()
+    bad[17] = t2[0]
+    bad[400] = t2[0]
+    sc2 = sc.copy()
+    sc2[17] = 0
+    sc2[17, 0] = 7                      # odd multiple: contributes T2;  sc2[400] stays random
+    want2 = O.jac_to_affine(O.ark_msm(bad, sc2))
+    e = M.Engine(0)
+    with pytest.raises(M.MsmError, match="-3"):
+        e.set_bases(bad)
+    e.close()
+    for tables in (0, 1, 3):
+        e = M.Engine(0, tables=tables)
+        e.set_bucket_arithmetic(True)
+        e.set_bases(bad)
+        assert np.array_equal(O.jac_to_affine(e.msm_host(sc2)), want2), tables
+        e.close()
+    # one-call form: refused by default, exact under B200MSM_GROUP=xyzz
+    M.VariableBaseMSM.release()
+    with pytest.raises(M.MsmError):
+        M.VariableBaseMSM.multi_scalar_mul(bad, sc2)
+    os.environ["B200MSM_GROUP"] = "xyzz"
+    try:
+        M.VariableBaseMSM.release()
+        assert np.array_equal(O.jac_to_affine(M.VariableBaseMSM.multi_scalar_mul(bad, sc2)), want2)
+    finally:
+        del os.environ["B200MSM_GROUP"]
+        M.VariableBaseMSM.release()
+
+
+@pytest.mark.parametrize("k", [3, 0])
+def test_golden_vectors_with_xyzz_buckets_on_bls12_377(M, oracle, golden_instances, k):
+    """The arkworks vectors through the second bucket arithmetic of BLS12-377 (b200msm_set_bucket_arithmetic)."""
+    g = golden_instances[k]
+    e = M.Engine(0)
+    e.set_bucket_arithmetic(True)
+    e.set_bases(g["aff"])
+    out = e.msm_host(g["scalars"])
+    assert oracle.compress(oracle.jac_to_affine(out)).tobytes() == g["result"]
+    e.close()
+
+
+def test_all_zero_record_is_infinity_in_96_byte_points(M, oracle):
+    """Flag-less 96-byte blst_p1_affine records encode infinity as x = y = 0 (sppark affine_t::is_inf, ec/xyzz_t.hpp:44-45):
+    mult_pippenger, VariableBaseMSM(stride=96) and Engine.set_bases(stride=96) must skip such a base, on both curves."""
+    O = oracle
+    n = 700
+    for curve in (0, 1):
+        pts, sc = O.gen_points(n, seed=61, curve=curve), O.gen_scalars(n, seed=62, curve=curve)
+        ref = pts.copy()
+        for i in (0, 33, 699):
+            ref[i] = 0
+            ref[i, 96] = 1                                                # the oracle sees a flagged infinity
+        want = O.jac_to_affine(O.ark_msm(ref, sc, curve), curve)
+        p96 = np.ascontiguousarray(pts[:, :96]).copy()
+        p96[[0, 33, 699]] = 0                                             # the library sees all-zero records
+        got = M.VariableBaseMSM.multi_scalar_mul(p96, sc, curve=curve, stride=96)
+        assert np.array_equal(O.jac_to_affine(got, curve), want), curve
+        e = M.Engine(curve, tables=3)
+        e.set_bases(p96, stride=96)
+        assert np.array_equal(O.jac_to_affine(e.msm_host(sc), curve), want), curve
+        e.close()
+        if curve == 0:
+            assert np.array_equal(O.jac_to_affine(M.multi_scalar_mult_blst(p96, sc)), want)
+    M.VariableBaseMSM.release()
+
+
+def test_stage_times_cover_every_chunk(M, oracle, monkeypatch):
+    """b200msm_get_stage_ms after a chunked msm_host: the accumulate time is the sum over the chunks (one event set per
+    chunk), not the last chunk's."""
+    import torch
+    n = 1 << 20
+    e = M.Engine(0)
+    e.set_bases_generated(n, seed=5, mode=0, distinct=1 << 12)
+    sc = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    e.generate_scalars(sc.data_ptr(), n, 9)
+    out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    e.msm_device(sc.data_ptr(), n, out.data_ptr())
+    e.sync()
+    one = e.stage_ms()
+    host = sc.cpu().numpy()
+    monkeypatch.setenv("B200MSM_HOST_CHUNKS", "4")
+    e2 = M.Engine(0)
+    e2.set_bases_generated(n, seed=5, mode=0, distinct=1 << 12)
+    r = e2.msm_host(host)
+    four = e2.stage_ms()
+    assert np.array_equal(oracle.jac_to_affine(r), oracle.jac_to_affine(out.cpu().numpy()))
+    assert 0.7 * one["accumulate"] < four["accumulate"] < 1.6 * one["accumulate"], (one, four)
+    assert four["digits_hist"] < 5 * one["digits_hist"] + 1.0, (one, four)      # no longer "everything since the call began"
+    e.close()
+    e2.close()

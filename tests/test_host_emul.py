@@ -17,14 +17,31 @@ from oracle import ref_bigint as RB
 HERE = os.path.join(ROOT, "tests", "host_emul")
 
 
-@pytest.fixture(scope="module")
-def emul():
-    so = os.path.join(HERE, "emul.so")
+def _build_emul(name, flags):
+    so = os.path.join(HERE, name)
     src = os.path.join(HERE, "emul.cpp")
     hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "ec.cuh", "te.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++", src, "-o", so])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++"] + flags + [src, "-o", so])
+    return so
+
+
+def _hot_flags():
+    """The -D switches the hot translation unit of the library is compiled with (csrc/Makefile HOT_DEFS): the host build
+    must emulate the same Te::madd."""
+    mk = open(os.path.join(ROOT, "2022-entries_b200", "csrc", "Makefile")).read()
+    for line in mk.splitlines():
+        if line.startswith("HOT_DEFS"):
+            return line.split("=", 1)[1].split()
+    return []
+
+
+@pytest.fixture(scope="module", params=["hot", "plain"])
+def emul(request):
+    """Two host builds: with the hot kernels' switches (what k_accumulate runs) and without (what the cold kernels run)."""
+    so = _build_emul("emul.so", _hot_flags()) if request.param == "hot" else _build_emul("emul_plain.so", [])
     L = ctypes.CDLL(so)
+    L.emul_fp_mul_raw.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
     vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     L.emul_fp_op.argtypes = [i32, i32, vp, vp, vp, sz]
     L.emul_ec_op.argtypes = [i32, i32, vp, vp, sz, i32]
@@ -103,6 +120,34 @@ def test_lazy_multiply_bound(emul, oracle, curve, k1, k2):
     r = np.zeros_like(a)
     assert emul.emul_fp_mul_lazy(curve, _p(a), _p(b), _p(r), n, k1, k2) == 0
     assert np.array_equal(r.reshape(-1, 48), oracle.fp_op(oracle.FP_MUL, a, b, curve))
+
+
+@pytest.mark.parametrize("la,lb", [(3, 1), (3, 2), (2, 3), (1, 1), (6, 1)])
+def test_multiplier_accepts_unnormalised_limbs(emul, la, lb):
+    """Te::madd (TE_LAZY_NORM) hands the multiplier sums whose limbs were not carried: limbs 0..12 up to la * 2^28 and
+    lb * 2^28 with la * lb <= 6 (te.cuh).  Worst case (every limb at its bound) and random fills: the result must be the
+    Montgomery product of the VALUES, normalised -- i.e. no 64-bit column overflowed."""
+    rng = np.random.default_rng(la * 10 + lb)
+    p = RB.CURVES[0]["p"]
+    n = 64
+    A = rng.integers(0, la << 28, size=(n, 14), dtype=np.uint64).astype(np.uint32)
+    B = rng.integers(0, lb << 28, size=(n, 14), dtype=np.uint64).astype(np.uint32)
+    A[0, :13] = (la << 28) - 1
+    B[0, :13] = (lb << 28) - 1
+    A[1, :13] = (la << 28) - 1
+    B[2, :13] = (lb << 28) - 1
+    A[:, 13] = rng.integers(0, 1 << 17, size=n)            # the top limb is bounded by the value, not by the carry state
+    B[:, 13] = rng.integers(0, 1 << 17, size=n)
+    R = np.zeros((n, 14), np.uint32)
+    emul.emul_fp_mul_raw(0, _p(A), _p(B), _p(R), n)
+    rinv = pow(1 << 392, -1, p)
+    for i in range(n):
+        va = sum(int(A[i, j]) << (28 * j) for j in range(14))
+        vb = sum(int(B[i, j]) << (28 * j) for j in range(14))
+        vr = sum(int(R[i, j]) << (28 * j) for j in range(14))
+        assert all(int(R[i, j]) < (1 << 28) for j in range(13)), "result not normalised"
+        assert vr % p == va * vb * rinv % p
+        assert vr < va * vb // (1 << 392) + p + 1
 
 
 def _xyzz_from_aff(O, aff, curve):
