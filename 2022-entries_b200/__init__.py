@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("B200MSM_LIB") or os.path.join(_HERE, "libb200msm.so")
 BLS12_377, BLS12_381 = 0, 1
 BASES_HARNESS, BASES_DISTINCT = 0, 1
 AFFINE_BYTES, SCALAR_BYTES, PROJECTIVE_BYTES = 104, 32, 144
+PEER_HANDLE_BYTES = 320      # one rank's handle for the multi-GPU bucket reduce-scatter (b200msm_peer_export)
 PARTIAL_BYTES = 224          # one GPU's partial result: XYZZ in the device representation (4 x 14 x 28-bit limbs)
 XYZZ_ABI_BYTES = 192         # test entry points: XYZZ as 4 arkworks field elements
 ENTRY_BYTES = {BLS12_377: 144, BLS12_381: 112}      # one base-table entry in device memory (csrc/grp.cuh)
@@ -66,6 +67,15 @@ def lib():
     L.b200msm_combine_device.argtypes = [vp, vp, i32, vp]
     L.b200msm_msm_partial_host.argtypes = [vp, vp, u64, vp]
     L.b200msm_sync.argtypes = [vp]
+    L.b200msm_peer_export.argtypes = [vp, i32, vp]
+    L.b200msm_peer_attach.argtypes = [vp, i32, i32, vp]
+    L.b200msm_peer_detach.argtypes = [vp]
+    L.b200msm_peer_info.argtypes = [vp, ctypes.POINTER(u64)]
+    L.b200msm_msm_peer_partial_device.argtypes = [vp, vp, u64, vp]
+    L.b200msm_msm_peer_partial_host.argtypes = [vp, vp, u64, vp]
+    L.b200msm_peer_accumulate_device.argtypes = [vp, vp, u64]
+    L.b200msm_peer_reduce.argtypes = [vp, vp]
+    L.b200msm_check_bases_in_g1.argtypes = [vp, ctypes.POINTER(u64)]
     L.b200msm_variable_base_msm.argtypes = [i32, i32, vp, u64, u64, vp, u64, vp]
     L.b200msm_variable_base_release.argtypes = []
     L.mult_pippenger.argtypes = [vp, vp, sz, vp]
@@ -99,7 +109,9 @@ def lib():
 EXPORTED_SYMBOLS = [
     "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bucket_arithmetic", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
-    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync", "b200msm_get_info", "b200msm_plan_info",
+    "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync",
+    "b200msm_peer_export", "b200msm_peer_attach", "b200msm_peer_detach", "b200msm_peer_info", "b200msm_msm_peer_partial_device", "b200msm_msm_peer_partial_host",
+    "b200msm_peer_accumulate_device", "b200msm_peer_reduce", "b200msm_check_bases_in_g1", "b200msm_get_info", "b200msm_plan_info",
     "b200msm_get_stage_ms", "b200msm_reset_stage_stats", "b200msm_get_stage_ms_sum", "b200msm_test_fp_op", "b200msm_test_ec_op", "b200msm_test_grp_op", "mult_pippenger_init", "mult_pippenger_inf",
     "mult_pippenger_free", "b200msm_variable_base_msm", "b200msm_variable_base_release", "mult_pippenger", "MSMAllocContext", "MSMFreeContext", "MSMPreprocessPoints", "MSMRun",
 ]
@@ -331,6 +343,44 @@ class Engine:
     def msm_partial_host(self, scalars_host_ptr, n, out_xyzz_dev_ptr):
         """scalars_host_ptr: address of n * 32 bytes of (pinned) host memory, valid until sync()."""
         self._ck(lib().b200msm_msm_partial_host(self.h, ctypes.c_void_p(scalars_host_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_partial_host")
+
+    # ---- multi-GPU bucket reduce-scatter (include/b200msm.h "b200msm_peer_*")
+    def peer_export(self, chunks=1):
+        h = np.zeros(PEER_HANDLE_BYTES, np.uint8)
+        self._ck(lib().b200msm_peer_export(self.h, chunks, _ptr(h)), "peer_export")
+        return h
+
+    def peer_attach(self, rank, world, handles):
+        hs = _as_u8(handles, PEER_HANDLE_BYTES, "handles")
+        if hs.size != world * PEER_HANDLE_BYTES:
+            raise MsmError("peer_attach: one handle per rank")
+        self._ck(lib().b200msm_peer_attach(self.h, rank, world, _ptr(hs)), "peer_attach")
+
+    def peer_detach(self):
+        self._ck(lib().b200msm_peer_detach(self.h), "peer_detach")
+
+    def peer_info(self):
+        a = (ctypes.c_uint64 * 4)()
+        lib().b200msm_peer_info(self.h, a)
+        return dict(zip(("world", "rank", "chunks", "nvlink_bytes"), [int(v) for v in a]))
+
+    def msm_peer_partial_device(self, scalars_dev_ptr, n, out_xyzz_dev_ptr):
+        self._ck(lib().b200msm_msm_peer_partial_device(self.h, ctypes.c_void_p(scalars_dev_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_peer_partial_device")
+
+    def msm_peer_partial_host(self, scalars_host_ptr, n, out_xyzz_dev_ptr):
+        self._ck(lib().b200msm_msm_peer_partial_host(self.h, ctypes.c_void_p(scalars_host_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_peer_partial_host")
+
+    def peer_accumulate_device(self, scalars_dev_ptr, n):
+        self._ck(lib().b200msm_peer_accumulate_device(self.h, ctypes.c_void_p(scalars_dev_ptr), n), "peer_accumulate_device")
+
+    def peer_reduce(self, out_xyzz_dev_ptr):
+        self._ck(lib().b200msm_peer_reduce(self.h, ctypes.c_void_p(out_xyzz_dev_ptr)), "peer_reduce")
+
+    def check_bases_in_g1(self):
+        """Number of resident bases outside the prime-order subgroup (r * P != infinity); opt-in, ~380 curve operations per base."""
+        k = ctypes.c_uint64()
+        self._ck(lib().b200msm_check_bases_in_g1(self.h, ctypes.byref(k)), "check_bases_in_g1")
+        return int(k.value)
 
     def combine_device(self, xyzz_dev_ptr, count, out_dev_ptr):
         self._ck(lib().b200msm_combine_device(self.h, ctypes.c_void_p(xyzz_dev_ptr), count, ctypes.c_void_p(out_dev_ptr)), "combine_device")

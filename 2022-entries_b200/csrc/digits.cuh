@@ -66,8 +66,11 @@ DG_D void for_each_digit(const uint32_t *__restrict__ scalars, uint32_t i, uint3
         s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w; s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
     }
     uint32_t(&s8)[8] = reinterpret_cast<uint32_t(&)[8]>(s);
-    if (s[7] >= C::r(7)) ScalarOps<C>::mod_r(s8);      // top word below r's: already reduced (every harness scalar is)
-    bool neg = ScalarOps<C>::fold_top_bit(s8);
+    bool neg = false;
+    if (C::FOLD_SCALAR) {
+        if (s[7] >= C::r(7)) ScalarOps<C>::mod_r(s8);  // top word below r's: already reduced (every harness scalar is)
+        neg = ScalarOps<C>::fold_top_bit(s8);
+    }
     s[8] = 0;
     const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
     uint32_t carry = 0;

@@ -45,7 +45,9 @@ struct fp_abi { uint32_t w[12]; };          // arkworks Fq: 6 x u64 little-endia
 // table below from p with Python integers).  constexpr accessors so unrolled code sees immediates.
 struct Bls12_377 {
     static constexpr int ID = 0;
-    static constexpr int SCALAR_BITS = 253;
+    static constexpr int SCALAR_BITS = 253;          // bits of r
+    static constexpr int WINDOW_BITS = 253;          // bits the window plan covers: the scalar is first reduced mod r and its top bit
+    static constexpr bool FOLD_SCALAR = true;        // folded away (s -> r - s, point negated) -- both valid only for points of order r
     static constexpr uint32_t INV = 0xfffffffu;      // -p^-1 mod 2^28
     static constexpr uint32_t P0INV = 0x0000001u;    //  p^-1 mod 2^28
     FP_HD static constexpr uint32_t p(int i) {
@@ -104,11 +106,17 @@ struct Bls12_377 {
 // at 8 M + 2 S per mixed add instead of 7 M.  Selected per context (b200msm_set_bucket_arithmetic / B200MSM_GROUP=xyzz).
 struct Bls12_377_sw : Bls12_377 {
     static constexpr bool HAS_TE = false;
+    // arkworks multiplies the INTEGER scalar into the point (no reduction mod r): for a base outside G1, r P != 0, so neither
+    // `s mod r` nor the top-bit fold is allowed.  This arithmetic walks all 256 scalar bits (+ 1 for the last signed carry).
+    static constexpr int WINDOW_BITS = 257;
+    static constexpr bool FOLD_SCALAR = false;
 };
 
 struct Bls12_381 {
     static constexpr int ID = 1;
     static constexpr int SCALAR_BITS = 255;
+    static constexpr int WINDOW_BITS = 255;
+    static constexpr bool FOLD_SCALAR = true;
     static constexpr uint32_t INV = 0xffcfffdu;
     static constexpr uint32_t P0INV = 0x0030003u;
     FP_HD static constexpr uint32_t p(int i) {

@@ -34,6 +34,9 @@ template <class C> struct GrpXyzz {
     }
     __device__ __noinline__ static void add_ni(xyzz_t &a, const xyzz_t &b) { Ec<C>::add(a, b); }
     __device__ __noinline__ static void dbl_ni(xyzz_t &a) { Ec<C>::dbl(a); }
+    // acc += the table entry at e (global memory); cold kernels only
+    __device__ __noinline__ static void madd_entry_ni(xyzz_t &acc, const entry_t *e, bool /*ark*/) { madd_staged(acc, reinterpret_cast<const uint4 *>(e), 1, false); }
+    __device__ static bool is_neutral(const xyzz_t &a) { return Ec<C>::is_inf(a); }
     __device__ static bool to_sw_affine(fp &x, fp &y, const xyzz_t &a) {
         if (Ec<C>::is_inf(a)) return false;
         Ec<C>::to_affine_ni(x, y, a);
@@ -87,6 +90,17 @@ template <class C> struct GrpTe {
     }
     __device__ __noinline__ static void add_ni(xyzz_t &a, const xyzz_t &b) { Te<C>::add(a, b); }
     __device__ __noinline__ static void dbl_ni(xyzz_t &a) { Te<C>::dbl(a); }
+    __device__ __noinline__ static void madd_entry_ni(xyzz_t &acc, const entry_t *e, bool ark) {
+        te_pre_t q;
+        Te<C>::unpack(q, *e, ark);
+        Te<C>::madd(acc, q);
+    }
+    // (0 : 1 : 1) exactly: X = 0 also holds for the point of order 2, (0 : -1 : 1)
+    __device__ static bool is_neutral(const xyzz_t &a) {
+        fp t;
+        F::template sub<3>(t, a.y, a.zz);
+        return F::is_zero(a.x) && F::is_zero(t);
+    }
     __device__ __noinline__ static bool to_sw_affine(fp &x, fp &y, const xyzz_t &a) {
         if (Te<C>::is_inf(a)) return false;
         fp zmy, zpy, den, inv, t, one, c3, cy;

@@ -35,25 +35,52 @@ template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh);
 // the cheaper of the two walks is chosen: serial costs max(pieces) adds, cooperative costs sum(pieces/32 + 6) over the
 // lanes with more than BIG_BUCKET_PIECES pieces.  Uniform scalars with a full top window never enter this path.
 #define BIG_BUCKET_PIECES 8
+// Multi-GPU bucket reduce-scatter (SURVEY.md 8e asks for one exchange of partial sums; this is the exchange done where the
+// data is consumed): with point sharding every GPU holds partial sums of ALL buckets.  GPU g reduces only the buckets
+// [g nb / G, (g + 1) nb / G), reading every peer's partial sums of that slice straight from the peer's HBM over NVLink
+// (mapped pointers in srcs) inside this kernel -- the loads of one thread's next source overlap the curve additions of the
+// other warps, there is no staging copy and no separate collective.  Cross-GPU ordering is two counters per pair:
+// `ready` (my bucket sums of epoch e are complete; set by k_peer_signal after k_accumulate) is awaited here before the first
+// remote load, `done` (I have finished reading yours) is awaited by the peer before it overwrites them (k_peer_wait).
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 16-byte loads that bypass the non-coherent path: the record may live in a peer GPU's memory and was written during this launch's wait
+__device__ __forceinline__ void load_xyzz_cv(xyzz_t &d, const xyzz_t *src) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *t = reinterpret_cast<uint4 *>(&d);
+#pragma unroll
+    for (int i = 0; i < XYZZ_VEC; i++) t[i] = __ldcv(s + i);
+}
 template <class C, bool INDIRECT>
-__global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const uint32_t *__restrict__ piece_off, uint32_t m,
+__global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const red_src_t *__restrict__ srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t m,
                                                        xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT,
-                                                       uint32_t nchunks, size_t res_stride, size_t poff_stride) {
+                                                       const uint32_t *__restrict__ wait_flags, uint32_t wait_n, uint32_t epoch) {
     __shared__ xyzz_t sh[64];
     __shared__ xyzz_t shw[INDIRECT ? 4 : 1][INDIRECT ? 17 : 1];     // per warp: 16 tree slots + 1 hand-over slot
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;      // the grid covers the outputs exactly
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (INDIRECT && wait_flags) {                                   // peers' bucket sums of this epoch must be complete
+        if (threadIdx.x < wait_n)
+            while ((int32_t)(ld_acquire_sys(wait_flags + threadIdx.x) - epoch) < 0) __nanosleep(100);
+        __syncthreads();
+    }
     xyzz_t run, tot, b;
     Grp<C>::set_inf(run);
     Grp<C>::set_inf(tot);
     for (uint32_t jj = m; jj-- > 0;) {
-        uint32_t k = t * m + jj;
+        uint32_t k = bucket_base + t * m + jj;
         if (jj + 1 < m) Grp<C>::add_ni(tot, run);                   // after the loop: tot = sum_j j * B_j
-        if (INDIRECT) {        // a bucket = the sum of its pieces, over every chunk the point set was accumulated in
-            for (uint32_t ch = 0; ch < nchunks; ch++) {
-                const uint32_t *po = piece_off + ch * poff_stride;
-                const uint32_t p0 = po[k], p1 = po[k + 1];
-                const xyzz_t *src = in + ch * res_stride;
+        if (INDIRECT) {        // a bucket = the sum of its pieces, over every chunk the point set was accumulated in, on every GPU
+            for (uint32_t ch = 0; ch < nsrc; ch++) {
+                const uint32_t *po = srcs[ch].poff;
+                const uint32_t p0 = __ldcv(po + k), p1 = __ldcv(po + k + 1);
+                const xyzz_t *src = srcs[ch].res;
                 bool big = (blockDim.x & 31) == 0 && p1 - p0 > BIG_BUCKET_PIECES;            // whole warps only
                 uint32_t todo = __ballot_sync(0xffffffffu, big);
                 if (todo) {                                         // serial: max(pieces); cooperative: sum(pieces / 32 + 6)
@@ -72,14 +99,14 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
                     const uint32_t q0 = __shfl_sync(0xffffffffu, p0, owner), q1 = __shfl_sync(0xffffffffu, p1, owner);
                     xyzz_t part;
                     Grp<C>::set_inf(part);
-                    for (uint32_t q = q0 + lane; q < q1; q += 32) { load_xyzz(b, src + q); Grp<C>::add_ni(part, b); }
+                    for (uint32_t q = q0 + lane; q < q1; q += 32) { load_xyzz_cv(b, src + q); Grp<C>::add_ni(part, b); }
                     warp_sum<C>(part, shw[warp]);
                     if (lane == 0) store_xyzz(&shw[warp][16], part);
                     __syncwarp();
                     if ((int)lane == owner) { load_xyzz(b, &shw[warp][16]); Grp<C>::add_ni(run, b); }
                     __syncwarp();
                 }
-                if (!big) for (uint32_t q = p0; q < p1; q++) { load_xyzz(b, src + q); Grp<C>::add_ni(run, b); }
+                if (!big) for (uint32_t q = p0; q < p1; q++) { load_xyzz_cv(b, src + q); Grp<C>::add_ni(run, b); }
             }
         } else {
             load_xyzz(b, in + k);
@@ -146,10 +173,11 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_
             Grp<C>::set_inf(v);
             if ((uint32_t)lane < tm.n) {
                 load_xyzz(v, tm.arr + (size_t)f * tm.stride_f + lane);
-                if (tm.kind == 1) {         // lane * v by double-and-add over 5 bits
+                if (tm.kind == 1) {         // (base + lane) * v by double-and-add over 5 bits (base + n <= 32)
                     xyzz_t r;
                     Grp<C>::set_inf(r);
-                    for (int b = 4; b >= 0; b--) { Grp<C>::dbl_ni(r); if ((lane >> b) & 1) Grp<C>::add_ni(r, v); }
+                    const uint32_t wgt = tm.base + lane;
+                    for (int b = 4; b >= 0; b--) { Grp<C>::dbl_ni(r); if ((wgt >> b) & 1) Grp<C>::add_ni(r, v); }
                     v = r;
                 }
             }
@@ -235,6 +263,26 @@ template <class C>
 __global__ void __launch_bounds__(128) k_make_entries(const affine_t *__restrict__ src, uint32_t n, typename Grp<C>::entry_t *__restrict__ dst, bool ark,
                                                       const uint32_t *__restrict__ infmask, uint32_t *__restrict__ bad) {
     Grp<C>::make_entries(src, n, dst, blockIdx.x * blockDim.x + threadIdx.x, ark, infmask, bad);
+}
+// Opt-in subgroup check (b200msm_check_bases_in_g1): r * P_i for every base through the bucket arithmetic's own doubling and
+// mixed add on table 0 (253 / 255 doublings + popcount(r) mixed adds per point: seconds at 2^26, init time only); counts the
+// bases whose multiple is not the neutral element.  arkworks makes the same check when it deserialises a G1Affine
+// (P1B/nickray/driver/algebra/ec/src/models/short_weierstrass_jacobian.rs is_in_correct_subgroup_assuming_on_curve).
+template <class C>
+__global__ void __launch_bounds__(128) k_check_order_r(const typename Grp<C>::entry_t *__restrict__ entries, const uint32_t *__restrict__ infmask, uint32_t n, bool ark,
+                                                       uint32_t *__restrict__ outside) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || ((infmask[i >> 5] >> (i & 31)) & 1)) return;
+    xyzz_t acc;
+    Grp<C>::set_inf(acc);
+    for (int b = C::SCALAR_BITS - 1; b >= 0; b--) {
+        Grp<C>::dbl_ni(acc);
+        uint32_t word = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) if (w == (b >> 5)) word = C::r(w);
+        if ((word >> (b & 31)) & 1) Grp<C>::madd_entry_ni(acc, entries + i, ark);
+    }
+    if (!Grp<C>::is_neutral(acc)) atomicAdd(outside, 1u);
 }
 // tmp[i] = 2^k * src[i]  (XYZZ, not normalised)
 template <class C>

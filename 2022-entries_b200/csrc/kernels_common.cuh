@@ -7,6 +7,15 @@
 
 namespace b200msm {
 
+__device__ __forceinline__ uint32_t ld_acquire_sys_c(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_c(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // exclusive prefix sum of uint32 (three launches; blocks of 256 threads x 8 elements)
 #define SCAN_TPB 256
@@ -180,6 +189,21 @@ __global__ void __launch_bounds__(BINSC_TPB) k_bin_scatter(const uint2 *__restri
     for (int k = 0; k < BINSC_EPT; k++) slot[k] = v[k].x != 0xffffffffu ? atomicAdd(&cursor[v[k].x], 1u) : 0;
 #pragma unroll
     for (int k = 0; k < BINSC_EPT; k++) if (v[k].x != 0xffffffffu) refs[slot[k]] = v[k].y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU bucket reduce-scatter: the two cross-GPU counters (protocol at k_reduce_slices, kernels_cold.cuh)
+// slot = this GPU's rank: flags[slot] of every peer (peer_flags[p] = peer p's flag array, mapped) <- epoch
+__global__ void k_peer_signal(uint32_t *const *__restrict__ peer_flags, uint32_t world, uint32_t slot, uint32_t epoch) {
+    if (threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys_c(peer_flags[threadIdx.x] + slot, epoch);
+    }
+}
+// returns when every one of flags[0 .. world) has reached epoch (wrap-safe comparison)
+__global__ void k_peer_wait(const uint32_t *__restrict__ flags, uint32_t world, uint32_t epoch) {
+    if (threadIdx.x < world)
+        while ((int32_t)(ld_acquire_sys_c(flags + threadIdx.x) - epoch) < 0) __nanosleep(100);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,7 +7,12 @@
 namespace b200msm {
 
 #define FIN_MAX_TERMS 24
-struct fin_term_t { const xyzz_t *arr; uint32_t n; uint32_t stride_f; uint32_t shift; uint32_t kind; };
+struct fin_term_t { const xyzz_t *arr; uint32_t n; uint32_t stride_f; uint32_t shift; uint32_t kind; uint32_t base; };      // kind 1: element k weighs base + k
+// one source of bucket sums for the level-0 reduction: a chunk of this GPU's points, or (multi-GPU bucket reduce-scatter) a
+// chunk of a PEER GPU's points read over NVLink through a mapped pointer
+struct red_src_t { const xyzz_t *res; const uint32_t *poff; };
+#define RED_MAX_SRC 64
+#define PEER_MAX 32
 struct fin_args_t { fin_term_t term[FIN_MAX_TERMS]; int nterms; int F; int c; };
 #define NORM_BATCH 16
 #ifndef ACC_TPB
@@ -27,8 +32,11 @@ template <class C> struct LaunchHot {
 };
 template <class C> struct LaunchCold {
     // n_out threads in blocks of `block` (n_out % block == 0); outT gets one entry per block
-    static void reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT,
-                              uint32_t nchunks, size_t res_stride, size_t poff_stride);
+    // level 0 (srcs != nullptr): bucket k = bucket_base + output * m + j is the sum over nsrc sources of its pieces; with
+    // wait_flags the kernel first waits until wait_n peers have published `epoch` (their bucket sums are complete)
+    static void reduce_slices(cudaStream_t st, const xyzz_t *in, const red_src_t *srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t n_out, uint32_t block, uint32_t m,
+                              xyzz_t *outS, xyzz_t *outT, const uint32_t *wait_flags, uint32_t wait_n, uint32_t epoch);
+
     static void block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out);
     static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac);
     static void combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac);
@@ -39,6 +47,7 @@ template <class C> struct LaunchCold {
     static void convert_points(cudaStream_t st, const uint8_t *src, uint32_t n, uint32_t stride, affine_t *table0, uint32_t *infmask);
     static void export_points(cudaStream_t st, const void *entries, uint32_t n, uint32_t *dst, bool ark);
     static void make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark, const uint32_t *infmask, uint32_t *bad);
+    static void check_order_r(cudaStream_t st, const void *entries, const uint32_t *infmask, uint32_t n, bool ark, uint32_t *outside);
     static size_t entry_bytes();
     static void test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps);
     static void generator(fp &gx, fp &gy);      // host: the curve generator in the device representation

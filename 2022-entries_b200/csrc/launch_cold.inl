@@ -5,11 +5,12 @@
 namespace b200msm {
 
 template <class C>
-void LaunchCold<C>::reduce_slices(bool indirect, cudaStream_t st, const xyzz_t *in, const uint32_t *piece_off, uint32_t n_out, uint32_t block, uint32_t m, xyzz_t *outS, xyzz_t *outT,
-                                  uint32_t nchunks, size_t res_stride, size_t poff_stride) {
-    if (indirect) k_reduce_slices<C, true><<<n_out / block, block, 0, st>>>(in, piece_off, m, outS, outT, nchunks, res_stride, poff_stride);
-    else k_reduce_slices<C, false><<<n_out / block, block, 0, st>>>(in, nullptr, m, outS, outT, 1, 0, 0);
+void LaunchCold<C>::reduce_slices(cudaStream_t st, const xyzz_t *in, const red_src_t *srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t n_out, uint32_t block, uint32_t m,
+                                  xyzz_t *outS, xyzz_t *outT, const uint32_t *wait_flags, uint32_t wait_n, uint32_t epoch) {
+    if (srcs) k_reduce_slices<C, true><<<n_out / block, block, 0, st>>>(nullptr, srcs, nsrc, bucket_base, m, outS, outT, wait_flags, wait_n, epoch);
+    else k_reduce_slices<C, false><<<n_out / block, block, 0, st>>>(in, nullptr, 0, 0, m, outS, outT, nullptr, 0, 0);
 }
+
 template <class C> void LaunchCold<C>::block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out) {
     k_block_sum<C><<<ngroups, group < 128 ? group : 128, 0, st>>>(in, group, out);
 }
@@ -41,6 +42,9 @@ template <class C> void LaunchCold<C>::export_points(cudaStream_t st, const void
 }
 template <class C> void LaunchCold<C>::make_entries(cudaStream_t st, const affine_t *src, uint32_t n, void *dst_entries, bool ark, const uint32_t *infmask, uint32_t *bad) {
     k_make_entries<C><<<cdiv(cdiv(n, GRP_BATCH), 128), 128, 0, st>>>(src, n, (typename Grp<C>::entry_t *)dst_entries, ark, infmask, bad);
+}
+template <class C> void LaunchCold<C>::check_order_r(cudaStream_t st, const void *entries, const uint32_t *infmask, uint32_t n, bool ark, uint32_t *outside) {
+    k_check_order_r<C><<<cdiv(n, 128), 128, 0, st>>>((const typename Grp<C>::entry_t *)entries, infmask, n, ark, outside);
 }
 template <class C> size_t LaunchCold<C>::entry_bytes() { return sizeof(typename Grp<C>::entry_t); }
 template <class C> void LaunchCold<C>::test_grp(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out104, uint32_t n, int reps) {

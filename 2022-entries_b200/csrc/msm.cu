@@ -4,6 +4,7 @@
 // pippenger_t + pippenger_inf.cu, matter-labs msm.cu schedule_execution.  One context = one device, one set of
 // base tables, one stream; every MSM is the fixed kernel sequence in run_msm() below.
 #include <cuda_runtime.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
@@ -94,6 +95,21 @@ struct b200msm_ctx {
     uint64_t out_dev_cap = 0;
     std::vector<red_step_t> red_steps;
     fin_args_t fin;
+    red_src_t *src_tab = nullptr;    // device: sources of the level-0 reduction (this GPU's chunks, then the peers' chunks)
+    int src_tab_chunks = -1;         // chunk count the local table was last written for
+    // multi-GPU bucket reduce-scatter (b200msm_peer_*): rank g reduces buckets [g nb / G, (g + 1) nb / G) of every GPU
+    struct peer_t {
+        int rank = 0, world = 0, chunks = 1;
+        uint32_t epoch = 0;
+        uint32_t *flags = nullptr;           // this GPU's counters: ready[PEER_MAX], done[PEER_MAX] (peers write them over NVLink)
+        uint32_t **flag_ptrs = nullptr;      // device array: every peer's flag buffer, mapped
+        void *mapped[PEER_MAX][3] = {};      // cudaIpcOpenMemHandle results to close again
+        red_src_t *src_tab = nullptr;        // device: world x chunks sources
+        xyzz_t *red_buf = nullptr;
+        std::vector<red_step_t> steps;
+        fin_args_t fin;
+        uint64_t nvlink_bytes = 0;           // bytes one level-0 launch reads from peers (algorithmic)
+    } peer;
     // Stage boundaries: one event set per CHUNK (stages 0-3: digits, scatter, pieces, accumulate); the set of an MSM's
     // last chunk also takes the reduction and finalize boundaries (ev_last = 6) and closes the MSM.  A plain MSM is one set.
     static const int EV_RING = 64;
@@ -110,6 +126,13 @@ struct b200msm_ctx {
         fprintf(stderr, "b200msm: %s\n", msg.c_str());
         return code;
     }
+    void peer_release() {
+        for (auto &m : peer.mapped) for (void *&q : m) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+        void *ptrs[] = {peer.flags, peer.flag_ptrs, peer.src_tab, peer.red_buf};
+        for (void *q : ptrs) if (q) cudaFree(q);
+        peer.flags = nullptr; peer.flag_ptrs = nullptr; peer.src_tab = nullptr; peer.red_buf = nullptr;
+        peer.world = 0; peer.epoch = 0; peer.steps.clear();
+    }
     void free_plan() {
         void *ptrs[] = {tables, infmask, bad, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
                         scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1], bin_cursor, staging, raw_buf[0], raw_buf[1], sw_buf};
@@ -117,6 +140,9 @@ struct b200msm_ctx {
         tables = nullptr; infmask = nullptr; bad = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
         scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
         raw_buf[0] = raw_buf[1] = nullptr; sw_buf = nullptr; raw_cap = 0;
+        if (src_tab) cudaFree(src_tab);
+        src_tab = nullptr; src_tab_chunks = -1;
+        peer_release();
         red_steps.clear();
         n = 0;
         plan_ok = false;
@@ -124,14 +150,14 @@ struct b200msm_ctx {
     }
 };
 
-static int scalar_bits(int curve) { return curve == 0 ? Bls12_377::SCALAR_BITS : Bls12_381::SCALAR_BITS; }
+static int scalar_bits(int kind) { return kind == 0 ? Bls12_377::WINDOW_BITS : kind == 1 ? Bls12_381::WINDOW_BITS : Bls12_377_sw::WINDOW_BITS; }
 
 // ---------------------------------------------------------------------------------------------
 // window plan: choose c (window bits), T (tables) and F (folded windows) for n points.
 // cost model: W*n mixed adds (10 modmul) + 2 full adds (14 modmul) per bucket, buckets = F * 2^(c-1);
 // T limited by device memory (96 n bytes per table) and by the 31-bit point reference (T*n < 2^31).
 static bool choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
-    const int sb = scalar_bits(ctx->curve);
+    const int sb = scalar_bits(ctx->kind);
     uint64_t tmax_mem = (uint64_t)((double)free_bytes * 0.72 / ((double)ctx->entry_bytes * (double)n));
     uint64_t tmax_ref = ((1ull << 31) - 1) / n;
     uint64_t tmax = tmax_mem < tmax_ref ? tmax_mem : tmax_ref;
@@ -162,8 +188,62 @@ static bool choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
 
 template <class T> static cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
 
+// Bucket-reduction plan (see k_reduce_slices): level sizes, buffers carved from one allocation, the terms k_finalize sums.
+// div = 1: all buckets of this GPU.  div = G > 1 (bucket reduce-scatter, one folded window): the same tree restricted to the
+// rank-th 1/G of every level -- the slice of a level's outputs is the reduction of the slice of its inputs, so the only
+// place the position shows is the last level, whose 32 / G entries weigh (rank * 32 / G + k).
+static int make_red_plan(b200msm_ctx *ctx, uint32_t div, uint32_t rank, xyzz_t **buf_out, std::vector<red_step_t> &steps, fin_args_t &fin) {
+    struct lvl { uint32_t n_in, m, n_out, block, nT; };
+    std::vector<lvl> lv;
+    {
+        uint32_t cur = 1u << (ctx->c - 1);
+        bool first = true;
+        while (first || cur > 32) {
+            uint32_t m = cur >= 256 ? 8 : cur / 32;
+            if (m < 1) m = 1;
+            uint32_t n_out = cur / m / div, block = n_out < 128 ? n_out : 128;
+            if (n_out == 0 || (cur / m) % div) return ctx->fail(-1, "bucket reduce-scatter: the window is too small to split over this many GPUs");
+            lv.push_back({cur / div, m, n_out, block, n_out / block});
+            cur = cur / m;
+            first = false;
+        }
+    }
+    const uint32_t F = ctx->F;
+    size_t need = 0;
+    for (auto &l : lv) need += (size_t)F * (l.n_out + l.nT + (l.nT > 32 ? 32 : 0));
+    CK(dmalloc(buf_out, need + 1));
+    xyzz_t *bump = *buf_out;
+    auto take = [&](size_t cnt) { xyzz_t *p = bump; bump += cnt; return p; };
+    steps.clear();
+    memset(&fin, 0, sizeof(fin));
+    fin.F = ctx->F; fin.c = ctx->c;
+    const xyzz_t *cur_arr = nullptr;          // level 0 reads through the source table
+    uint32_t shift = 0;
+    for (size_t li = 0; li < lv.size(); li++) {
+        lvl &l = lv[li];
+        xyzz_t *S = take((size_t)F * l.n_out), *Tt = take((size_t)F * l.nT);
+        steps.push_back({li == 0 ? 0 : 1, cur_arr, F * l.n_out, l.block, l.m, S, Tt});
+        uint32_t nT = l.nT;
+        if (nT > 32) {
+            xyzz_t *T2 = take((size_t)F * 32);
+            steps.push_back({2, Tt, F * 32, 0, nT / 32, T2, nullptr});
+            Tt = T2; nT = 32;
+        }
+        if (fin.nterms >= FIN_MAX_TERMS - 2) return ctx->fail(-1, "reduction plan has too many terms");
+        fin.term[fin.nterms++] = {Tt, nT, nT, shift, 0, 0};              // 2^shift * sum_t T_t of this level
+        uint32_t lg = 0; while ((1u << lg) < l.m) lg++;
+        shift += lg;
+        cur_arr = S;
+    }
+    uint32_t last_n = lv.back().n_out;
+    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, 0, 0, 0};                     // sum of all buckets
+    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, shift, 1, rank * last_n};     // 2^shift * sum_k (base + k) * S_last[k]
+    return 0;
+}
+
 static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     if (ctx->plan_ok && ctx->n == n) return 0;        // same size again (one-shot calls): plan and buffers stand
+    int rc = 0;
     ctx->free_plan();
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -212,52 +292,8 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
         CK(dmalloc(&ctx->staging, (size_t)ctx->max_refs + 1));
     }
 
-    // bucket-reduction plan (see k_reduce_slices): sizes first, then carve red_buf
-    struct lvl { uint32_t n_in, m, n_out, block, nT; };
-    std::vector<lvl> lv;
-    {
-        uint32_t cur = 1u << (ctx->c - 1);
-        bool first = true;
-        while (first || cur > 32) {
-            uint32_t m = cur >= 256 ? 8 : cur / 32;
-            if (m < 1) m = 1;
-            uint32_t n_out = cur / m, block = n_out < 128 ? n_out : 128;
-            lv.push_back({cur, m, n_out, block, n_out / block});
-            cur = n_out;
-            first = false;
-        }
-    }
-    const uint32_t F = ctx->F;
-    size_t need = 0;
-    for (auto &l : lv) need += (size_t)F * (l.n_out + l.nT + (l.nT > 32 ? 32 : 0));
-    CK(dmalloc(&ctx->red_buf, need + 1));
-    xyzz_t *bump = ctx->red_buf;
-    auto take = [&](size_t cnt) { xyzz_t *p = bump; bump += cnt; return p; };
-    ctx->red_steps.clear();
-    fin_args_t &fin = ctx->fin;
-    memset(&fin, 0, sizeof(fin));
-    fin.F = ctx->F; fin.c = ctx->c;
-    const xyzz_t *cur_arr = ctx->res;
-    uint32_t shift = 0;
-    for (size_t li = 0; li < lv.size(); li++) {
-        lvl &l = lv[li];
-        xyzz_t *S = take((size_t)F * l.n_out), *Tt = take((size_t)F * l.nT);
-        ctx->red_steps.push_back({li == 0 ? 0 : 1, cur_arr, F * l.n_out, l.block, l.m, S, Tt});
-        uint32_t nT = l.nT;
-        if (nT > 32) {
-            xyzz_t *T2 = take((size_t)F * 32);
-            ctx->red_steps.push_back({2, Tt, F * 32, 0, nT / 32, T2, nullptr});
-            Tt = T2; nT = 32;
-        }
-        if (fin.nterms >= FIN_MAX_TERMS - 2) return ctx->fail(-1, "reduction plan has too many terms");
-        fin.term[fin.nterms++] = {Tt, nT, nT, shift, 0};                 // 2^shift * sum_t T_t of this level
-        uint32_t lg = 0; while ((1u << lg) < l.m) lg++;
-        shift += lg;
-        cur_arr = S;
-    }
-    uint32_t last_n = lv.back().n_out;
-    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, 0, 0};            // sum of all buckets
-    fin.term[fin.nterms++] = {cur_arr, last_n, last_n, shift, 1};        // 2^shift * W0(S_last)
+    CK(dmalloc(&ctx->src_tab, (size_t)RED_MAX_SRC));
+    rc = make_red_plan(ctx, 1, 0, &ctx->red_buf, ctx->red_steps, ctx->fin); if (rc) return rc;
     ctx->plan_ok = true;
     return 0;
 }
@@ -456,7 +492,12 @@ template <class C> static int run_chunk_t(b200msm_ctx *ctx, const void *scalars_
     }
     launches += 4;
     cudaEventRecord(ctx->ev[2], st);
-    // pieces
+    // pieces.  Bucket reduce-scatter: peers read piece_off / res of the previous MSM over NVLink -- nothing of them is overwritten
+    // before every peer has published `done` for that MSM.
+    if (ctx->peer.world && ctx->peer.epoch > 1 && chunk == 0) {
+        k_peer_wait<<<1, PEER_MAX, 0, st>>>(ctx->peer.flags + PEER_MAX, (uint32_t)ctx->peer.world, ctx->peer.epoch - 1);
+        launches++;
+    }
     k_scan_block_sums<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp);
     k_scan_top<<<1, 1024, 0, st>>>(ctx->scan_tmp, sblocks);
     k_scan_apply<1><<<sblocks, SCAN_TPB, 0, st>>>(ctx->counts, nb, lmax, ctx->scan_tmp, piece_off, nullptr);
@@ -477,16 +518,38 @@ template <class C> static int run_chunk_t(b200msm_ctx *ctx, const void *scalars_
     return 0;
 }
 // Stages 6-7: bucket reduction over the chunks' bucket sums, window combine, export.
-template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz) {
+// the level-0 source table of this GPU alone: entry ch = chunk ch's arrays, whatever number of chunks a call uses, so it is
+// written once per allocation of the arrays (a synchronising copy here would break the upload / compute overlap of msm_host)
+static int local_sources(b200msm_ctx *ctx, int nchunks) {
+    if (ctx->src_tab_chunks >= nchunks) return 0;
+    red_src_t h[RED_MAX_SRC];
+    const int cnt = ctx->chunks_alloc;
+    for (int ch = 0; ch < cnt; ch++) h[ch] = {ctx->res + (size_t)ch * ctx->max_pieces, ctx->piece_off + (size_t)ch * ((size_t)ctx->nbuckets + 1)};
+    CK(cudaMemcpy(ctx->src_tab, h, sizeof(red_src_t) * cnt, cudaMemcpyHostToDevice));
+    ctx->src_tab_chunks = cnt;
+    return 0;
+}
+// peer = false: every bucket of this GPU (nchunks sources).  peer = true: this rank's slice of the buckets of every GPU
+// (world x chunks sources over NVLink, waiting for the peers' `ready` counters inside the level-0 kernel).
+template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz, bool peer = false) {
     cudaStream_t st = ctx->stream;
     int launches = 0;
-    for (const red_step_t &s : ctx->red_steps) {
+    if (!peer) { int rc = local_sources(ctx, nchunks); if (rc) return rc; }
+    auto &P = ctx->peer;
+    for (const red_step_t &s : peer ? P.steps : ctx->red_steps) {
         if (s.kind == 2) LaunchCold<C>::block_sum(st, s.in, s.n_out, s.m, s.outS);
-        else LaunchCold<C>::reduce_slices(s.kind == 0, st, s.in, ctx->piece_off, s.n_out, s.block, s.m, s.outS, s.outT, (uint32_t)nchunks, ctx->max_pieces, (size_t)ctx->nbuckets + 1);
+        else if (s.kind == 1) LaunchCold<C>::reduce_slices(st, s.in, nullptr, 0, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
+        else if (!peer) LaunchCold<C>::reduce_slices(st, nullptr, ctx->src_tab, (uint32_t)nchunks, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
+        else {
+            LaunchCold<C>::reduce_slices(st, nullptr, P.src_tab, (uint32_t)(P.world * P.chunks), (uint32_t)P.rank * (ctx->nbuckets / (uint32_t)P.world), s.n_out, s.block, s.m,
+                                         s.outS, s.outT, P.flags, (uint32_t)P.world, P.epoch);
+            k_peer_signal<<<1, PEER_MAX, 0, st>>>(P.flag_ptrs, (uint32_t)P.world, PEER_MAX + (uint32_t)P.rank, P.epoch);      // done reading
+            launches++;
+        }
         launches++;
     }
     cudaEventRecord(ctx->ev[5], st);
-    LaunchCold<C>::finalize(st, ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac);
+    LaunchCold<C>::finalize(st, peer ? P.fin : ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac);
     launches++;
     cudaEventRecord(ctx->ev[6], st);
     ctx->ev_last[(ctx->ev_sets - 1) % b200msm_ctx::EV_RING] = 6;
@@ -500,9 +563,9 @@ static int run_chunk(b200msm_ctx *ctx, const void *scalars_dev, uint32_t first, 
     BY_GROUP(ctx->kind, rc = run_chunk_t<C>(ctx, scalars_dev, first, count, chunk));
     return rc;
 }
-static int run_reduce(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz) {
+static int run_reduce(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz, bool peer = false) {
     int rc = 0;
-    BY_GROUP(ctx->kind, rc = run_reduce_t<C>(ctx, nchunks, out_jac, out_xyzz));
+    BY_GROUP(ctx->kind, rc = run_reduce_t<C>(ctx, nchunks, out_jac, out_xyzz, peer));
     return rc;
 }
 // one MSM on the context's stream.  scalars: device, n x 32 bytes.  Exactly one of out_jac / out_xyzz is set.
@@ -514,14 +577,14 @@ static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, voi
 // piece_off / res hold one copy per chunk
 static int ensure_chunks(b200msm_ctx *ctx, int k) {
     if (k <= ctx->chunks_alloc) return 0;
+    if (ctx->peer.world) return ctx->fail(-1, "the bucket arrays are mapped by peer GPUs and cannot grow: attach with the chunk count the calls will use");
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->piece_off); cudaFree(ctx->res);
     ctx->piece_off = nullptr; ctx->res = nullptr;
     CK(dmalloc(&ctx->piece_off, (size_t)k * ((size_t)ctx->nbuckets + 1)));
     CK(dmalloc(&ctx->res, (size_t)k * ctx->max_pieces));
     ctx->chunks_alloc = k;
-    // the reduction plan reads level 0 from ctx->res
-    for (red_step_t &s : ctx->red_steps) if (s.kind == 0) s.in = ctx->res;
+    ctx->src_tab_chunks = -1;          // the level-0 source table points into the old arrays
     return 0;
 }
 
@@ -627,7 +690,31 @@ int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uin
     if (!affine_host || n == 0 || n >= (1ull << 31) || stride < 96 || (stride & 7)) return ctx->fail(-1, "b200msm_set_bases: bad argument");
     rc = alloc_plan(ctx, n); if (rc) return rc;
     BY_GROUP(ctx->kind, rc = set_bases_t<C>(ctx, affine_host, n, stride));
+    if (rc == 0 && ctx->kind != 2) {
+        const char *e = getenv("B200MSM_CHECK_G1");
+        if (e && atoi(e)) {              // opt-in: the default arithmetic folds scalars mod r, which is only right for bases of order r
+            uint64_t outside = 0;
+            rc = b200msm_check_bases_in_g1(ctx, &outside);
+            if (rc == 0 && outside) {
+                ctx->n = 0; ctx->plan_ok = false;
+                return ctx->fail(-3, std::to_string(outside) + " bases lie outside the prime-order subgroup; select the XYZZ bucket arithmetic (b200msm_set_bucket_arithmetic(ctx, 1) or B200MSM_GROUP=xyzz)");
+            }
+        }
+    }
     return rc;
+}
+
+int b200msm_check_bases_in_g1(b200msm_ctx *ctx, uint64_t *outside) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!outside || ctx->n == 0) return ctx->fail(-1, "b200msm_check_bases_in_g1: bad argument (bases not set)");
+    CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
+    BY_GROUP(ctx->kind, LaunchCold<C>::check_order_r(ctx->stream, ctx->tables, ctx->infmask, (uint32_t)ctx->n, ctx->acc_mix == 0, ctx->bad));
+    uint32_t cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, ctx->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
+    *outside = cnt;
+    return 0;
 }
 
 int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int mode, uint64_t distinct) {
@@ -687,11 +774,15 @@ int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, vo
 // chunk k+1 uploads while chunk k accumulates (each chunk into its own bucket sums, one shared reduction at the end).
 // Nothing else can hide the upload of the first batch of a call.  Stands in for the 1/4 + 3/4 split of the reference's
 // fastest entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).  buf: device staging of n x 32 bytes.
-static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_t n, uint8_t *buf, cudaEvent_t buf_free, void *out_jac, void *out_xyzz) {
-    int rc = 0;
+static int default_host_chunks(const b200msm_ctx *ctx, uint64_t n) {
     // measured: 4 chunks at 2^26 (294.5 -> 272.1 ms) and 2^25, 2 chunks at 2^23 (8 GPUs: 51.4 -> 48.4 ms end to end)
     int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : (n >= (1ull << 22) ? 2 : 1));
-    if (nch > 8) nch = 8;
+    return nch > 8 ? 8 : nch;
+}
+static int peer_clear_unused_chunks(b200msm_ctx *ctx, int used);
+static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_t n, uint8_t *buf, cudaEvent_t buf_free, void *out_jac, void *out_xyzz, bool peer = false) {
+    int rc = 0;
+    int nch = peer ? ctx->peer.chunks : default_host_chunks(ctx, n);
     if ((uint64_t)nch > n) nch = 1;
     if (nch > 1) { rc = ensure_chunks(ctx, nch); if (rc) return rc; }
     CK(cudaStreamWaitEvent(ctx->copy_stream, buf_free, 0));
@@ -710,6 +801,11 @@ static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_
         if (rc) return rc;
         used++;
     }
+    if (peer) {
+        rc = peer_clear_unused_chunks(ctx, used); if (rc) return rc;
+        k_peer_signal<<<1, PEER_MAX, 0, ctx->stream>>>(ctx->peer.flag_ptrs, (uint32_t)ctx->peer.world, (uint32_t)ctx->peer.rank, ctx->peer.epoch);
+        return run_reduce(ctx, ctx->peer.chunks, nullptr, out_xyzz, true);
+    }
     return run_reduce(ctx, used, out_jac, out_xyzz);
 }
 
@@ -719,6 +815,134 @@ int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_
     if (!ctx->scal_buf[0]) CK(cudaMalloc((void **)&ctx->scal_buf[0], (size_t)n * 32));
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
     return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev);
+}
+
+// ---- multi-GPU bucket reduce-scatter -------------------------------------------------------------------------------------
+// One process per GPU (or several contexts in one process: tests).  After b200msm_set_bases every rank exports a handle,
+// the handles are exchanged by the caller (torch.distributed all_gather in sharded.py), every rank attaches, and from then on
+// b200msm_msm_peer_partial_* replaces b200msm_msm_partial_*: the result is the sum over ALL GPUs' points of the buckets
+// of this rank's slice, still one 224-byte record, combined exactly as before (all-gather + b200msm_combine_device).
+struct peer_handle_t {
+    uint32_t magic, kind;
+    int32_t pid, device;
+    uint32_t c, F, nbuckets, max_pieces, chunks, pad;
+    uint64_t n;
+    uint64_t raw_res, raw_poff, raw_flags;          // the same process maps nothing: plain pointers
+    cudaIpcMemHandle_t res, poff, flags;
+};
+static_assert(sizeof(peer_handle_t) <= B200MSM_PEER_HANDLE_BYTES, "peer handle size");
+
+int b200msm_peer_export(b200msm_ctx *ctx, int chunks, void *handle_out) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!handle_out || chunks < 1 || chunks > 8 || !ctx->plan_ok) return ctx->fail(-1, "b200msm_peer_export: bad argument (bases not set?)");
+    if (ctx->F != 1) return ctx->fail(-1, "b200msm_peer_export: the bucket reduce-scatter needs a one-window plan (all windows folded)");
+    if (ctx->peer.world) return ctx->fail(-1, "b200msm_peer_export: already attached; detach first");
+    rc = ensure_chunks(ctx, chunks); if (rc) return rc;
+    if (!ctx->peer.flags) {
+        CK(dmalloc(&ctx->peer.flags, 2 * PEER_MAX));
+        CK(cudaMemset(ctx->peer.flags, 0, 2 * PEER_MAX * 4));
+    }
+    ctx->peer.chunks = chunks;
+    peer_handle_t h;
+    memset(&h, 0, sizeof(h));
+    h.magic = 0xb200feedu; h.kind = (uint32_t)ctx->kind; h.pid = (int32_t)getpid(); h.device = ctx->device;
+    h.c = (uint32_t)ctx->c; h.F = (uint32_t)ctx->F; h.nbuckets = ctx->nbuckets; h.max_pieces = ctx->max_pieces; h.chunks = (uint32_t)chunks; h.n = ctx->n;
+    h.raw_res = (uint64_t)ctx->res; h.raw_poff = (uint64_t)ctx->piece_off; h.raw_flags = (uint64_t)ctx->peer.flags;
+    CK(cudaIpcGetMemHandle(&h.res, ctx->res));
+    CK(cudaIpcGetMemHandle(&h.poff, ctx->piece_off));
+    CK(cudaIpcGetMemHandle(&h.flags, ctx->peer.flags));
+    memset(handle_out, 0, B200MSM_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int b200msm_peer_attach(b200msm_ctx *ctx, int rank, int world, const void *handles) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!handles || world < 2 || world > PEER_MAX || rank < 0 || rank >= world || !ctx->peer.flags) return ctx->fail(-1, "b200msm_peer_attach: bad argument (export first)");
+    if ((world & (world - 1)) || ctx->nbuckets % (uint32_t)world || ctx->peer.chunks * world > RED_MAX_SRC) return ctx->fail(-1, "b200msm_peer_attach: world must be a power of two dividing the bucket count");
+    auto &P = ctx->peer;
+    const uint8_t *hb = (const uint8_t *)handles;
+    red_src_t src[RED_MAX_SRC];
+    uint32_t *fl[PEER_MAX];
+    const size_t poff_stride = (size_t)ctx->nbuckets + 1;
+    for (int k = 0; k < world; k++) {
+        const int p = (rank + k) % world;              // own data first, then the peers in ring order: spreads the NVLink load
+        peer_handle_t h;
+        memcpy(&h, hb + (size_t)p * B200MSM_PEER_HANDLE_BYTES, sizeof(h));
+        if (h.magic != 0xb200feedu || h.kind != (uint32_t)ctx->kind || h.c != (uint32_t)ctx->c || h.F != 1 || h.nbuckets != ctx->nbuckets || h.max_pieces != ctx->max_pieces ||
+            h.chunks != (uint32_t)P.chunks || h.n != ctx->n)
+            return ctx->fail(-1, "b200msm_peer_attach: rank " + std::to_string(p) + " exported a different plan (every rank must hold the same number of points)");
+        const xyzz_t *res; const uint32_t *poff; uint32_t *flags;
+        if (p == rank) { res = ctx->res; poff = ctx->piece_off; flags = P.flags; }
+        else if (h.pid == (int32_t)getpid()) {         // another context of this process
+            res = (const xyzz_t *)h.raw_res; poff = (const uint32_t *)h.raw_poff; flags = (uint32_t *)h.raw_flags;
+            if (h.device != ctx->device) { cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError(); }
+        } else {
+            CK(cudaIpcOpenMemHandle(&P.mapped[p][0], h.res, cudaIpcMemLazyEnablePeerAccess));
+            CK(cudaIpcOpenMemHandle(&P.mapped[p][1], h.poff, cudaIpcMemLazyEnablePeerAccess));
+            CK(cudaIpcOpenMemHandle(&P.mapped[p][2], h.flags, cudaIpcMemLazyEnablePeerAccess));
+            res = (const xyzz_t *)P.mapped[p][0]; poff = (const uint32_t *)P.mapped[p][1]; flags = (uint32_t *)P.mapped[p][2];
+        }
+        for (int ch = 0; ch < P.chunks; ch++) src[k * P.chunks + ch] = {res + (size_t)ch * ctx->max_pieces, poff + (size_t)ch * poff_stride};
+        fl[p] = flags;
+    }
+    CK(dmalloc(&P.src_tab, (size_t)world * P.chunks));
+    CK(cudaMalloc((void **)&P.flag_ptrs, sizeof(uint32_t *) * PEER_MAX));
+    CK(cudaMemcpy(P.src_tab, src, sizeof(red_src_t) * world * P.chunks, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(P.flag_ptrs, fl, sizeof(uint32_t *) * world, cudaMemcpyHostToDevice));
+    P.rank = rank; P.world = world; P.epoch = 0;
+    rc = make_red_plan(ctx, (uint32_t)world, (uint32_t)rank, &P.red_buf, P.steps, P.fin); if (rc) { P.world = 0; return rc; }
+    P.nvlink_bytes = (uint64_t)(world - 1) * (ctx->nbuckets / (uint32_t)world) * (uint64_t)P.chunks * (sizeof(xyzz_t) + 8);
+    return 0;
+}
+
+int b200msm_peer_detach(b200msm_ctx *ctx) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->peer_release();
+    return 0;
+}
+
+int b200msm_peer_info(const b200msm_ctx *ctx, uint64_t info[4]) {
+    if (!ctx || !info) return -1;
+    info[0] = (uint64_t)ctx->peer.world; info[1] = (uint64_t)ctx->peer.rank; info[2] = (uint64_t)ctx->peer.chunks; info[3] = ctx->peer.nvlink_bytes;
+    return 0;
+}
+
+// chunks of a peer call the caller did not use hold no pieces, so that the peers' level-0 walk finds nothing there
+static int peer_clear_unused_chunks(b200msm_ctx *ctx, int used) {
+    for (int ch = used; ch < ctx->peer.chunks; ch++)
+        CK(cudaMemsetAsync(ctx->piece_off + (size_t)ch * ((size_t)ctx->nbuckets + 1), 0, ((size_t)ctx->nbuckets + 1) * 4, ctx->stream));
+    return 0;
+}
+// stages 1-5 on this GPU's points, then `ready` to every peer
+int b200msm_peer_accumulate_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_dev || ctx->n == 0 || n != ctx->n || !ctx->peer.world) return ctx->fail(-1, "b200msm_peer_accumulate_device: bad argument (not attached?)");
+    ctx->peer.epoch++;
+    rc = run_chunk(ctx, scalars_dev, 0, (uint32_t)ctx->n, 0); if (rc) return rc;
+    rc = peer_clear_unused_chunks(ctx, 1); if (rc) return rc;
+    k_peer_signal<<<1, PEER_MAX, 0, ctx->stream>>>(ctx->peer.flag_ptrs, (uint32_t)ctx->peer.world, (uint32_t)ctx->peer.rank, ctx->peer.epoch);
+    CK(cudaGetLastError());
+    return 0;
+}
+// this rank's slice of the buckets summed over every GPU (level 0 reads the peers over NVLink), reduced to one partial record
+int b200msm_peer_reduce(b200msm_ctx *ctx, void *out_xyzz_dev) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!out_xyzz_dev || !ctx->peer.world || ctx->peer.epoch == 0) return ctx->fail(-1, "b200msm_peer_reduce: bad argument");
+    return run_reduce(ctx, ctx->peer.chunks, nullptr, out_xyzz_dev, true);
+}
+int b200msm_msm_peer_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev) {
+    int rc = b200msm_peer_accumulate_device(ctx, scalars_dev, n); if (rc) return rc;
+    return b200msm_peer_reduce(ctx, out_xyzz_dev);
+}
+int b200msm_msm_peer_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (!scalars_host || !out_xyzz_dev || ctx->n == 0 || n != ctx->n || !ctx->peer.world) return ctx->fail(-1, "b200msm_msm_peer_partial_host: bad argument (not attached?)");
+    if (!ctx->scal_buf[0]) CK(cudaMalloc((void **)&ctx->scal_buf[0], (size_t)n * 32));
+    CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
+    ctx->peer.epoch++;
+    return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev, true);
 }
 
 int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uint64_t batches, void *out_jacobian_host) {

@@ -61,6 +61,22 @@ class CudaShardBackend:
     def combine(self, gathered, count, out):
         self.e.combine_device(gathered.data_ptr(), count, out.data_ptr())
 
+    # ---- bucket reduce-scatter over NVLink (b200msm_peer_*): optional, set up by ShardedMsm.attach_peers
+    def peer_export(self, chunks):
+        return torch.from_numpy(self.e.peer_export(chunks))
+
+    def peer_attach(self, rank, world, handles):
+        self.e.peer_attach(rank, world, handles.numpy())
+
+    def peer_detach(self):
+        self.e.peer_detach()
+
+    def peer_partial(self, scalars_dev, out):
+        self.e.msm_peer_partial_device(scalars_dev.data_ptr(), self.n, out.data_ptr())
+
+    def peer_partial_from_host(self, scalars_host, out):
+        self.e.msm_peer_partial_host(scalars_host.data_ptr(), self.n, out.data_ptr())
+
 
 class ShardedMsm:
     """multi_scalar_mult over G ranks.  Every rank calls msm() with ITS slice of the scalars and gets the full result."""
@@ -73,6 +89,36 @@ class ShardedMsm:
         self.partial = backend.new_buffer(backend.partial_bytes)
         self.gathered = backend.new_buffer(backend.partial_bytes * self.world)
         self.out = backend.new_buffer(backend.out_bytes)
+        self.peers = 0          # chunks the peer mapping was attached with; 0 = every rank reduces all of its own buckets
+
+    def attach_peers(self, chunks=1):
+        """Collective: switch to the bucket reduce-scatter -- rank g reduces the buckets [g B / G, (g + 1) B / G) of EVERY rank,
+        reading the peers' partial bucket sums over NVLink inside its level-0 reduction kernel (csrc/kernels_cold.cuh
+        k_reduce_slices).  The handles (CUDA IPC) travel through one all_gather on the group's default backend.
+        chunks: how many chunks a host-memory call splits its upload into (1 for device-resident scalars)."""
+        b = self.b
+        if self.world == 1 or not hasattr(b, "peer_export"):
+            return False
+        if self.peers:
+            self.detach_peers()
+        mine = b.peer_export(chunks)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine.numpy().tobytes(), group=self.group)
+        import numpy as np
+        handles = torch.from_numpy(np.frombuffer(b"".join(gathered), np.uint8).copy())
+        b.peer_attach(self.rank, self.world, handles)
+        dist.barrier(group=self.group)          # nobody runs a peer call before every rank has mapped every other rank
+        self.peers = chunks
+        return True
+
+    def detach_peers(self):
+        if self.peers:
+            stream = getattr(self.b, "stream", None)
+            if stream is not None:
+                stream.synchronize()
+            dist.barrier(group=self.group)      # every rank has finished reading this rank's buckets
+            self.b.peer_detach()
+            self.peers = 0
 
     def msm_device(self, scalars_dev, host=False):
         """scalars already on this rank's device (host=True: in pinned host memory, uploaded by the backend).
@@ -82,7 +128,11 @@ class ShardedMsm:
         if self.world == 1:
             b.full(b.upload(scalars_dev) if host else scalars_dev, self.out)
             return self.out
-        if host and hasattr(b, "partial_from_host"):
+        if self.peers and host:
+            b.peer_partial_from_host(scalars_dev, self.partial)
+        elif self.peers:
+            b.peer_partial(scalars_dev, self.partial)
+        elif host and hasattr(b, "partial_from_host"):
             b.partial_from_host(scalars_dev, self.partial)
         else:
             b.partial(b.upload(scalars_dev) if host else scalars_dev, self.partial)

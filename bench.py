@@ -36,6 +36,8 @@ METRIC = "BLS12-377 G1 MSM 2^{lg} points/s"
 WORKLOAD = ("BLS12-377 G1 MSM 2^{lg}, one batch, bases resident (harness generator shape: 2^15 distinct points replicated), "
             "uniform 253-bit scalars")
 SEED_BASES, SEED_SCALARS, DISTINCT = 77, 1234, 1 << 15
+TRAFFIC_FILE = "r01_traffic.json"      # ncu --set full capture behind roofline.traffic
+REF_SAMPLE_LOG_N = 22          # the CPU arm's sample, the same on every host
 
 
 def measured_peak_gbs():
@@ -108,6 +110,62 @@ def cpu_oracle_rate(O, log_sample, threads=None):
     return n / dt, dt
 
 
+def sweep_row(M, O, KA, torch, curve, lg, peak_gbs, warmup=2, steps=3):
+    """One size of the sweep: fresh engine, generated bases (2^15 distinct, replicated), closed-form check, CUDA-event timing."""
+    n = 1 << lg
+    e = M.Engine(curve)
+    try:
+        e.set_bases_generated(n, seed=SEED_BASES, mode=M.BASES_HARNESS, distinct=min(DISTINCT, n))
+        st = torch.cuda.Stream()
+        e.set_stream(st.cuda_stream)
+        sc = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+        out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+        e.generate_scalars(sc.data_ptr(), n, 5)
+        e.msm_device(sc.data_ptr(), n, out.data_ptr())
+        e.sync()
+        r_mod, t, rows = O.constants(curve)["r"], 0, 1 << 24
+        for a0 in range(0, n, rows):          # the scalars come back in pieces: 2^28 of them are 8.6 GB
+            k = min(rows, n - a0)
+            i = np.arange(a0, a0 + k, dtype=np.uint64)
+            logs = KA.splitmix64(np.uint64(SEED_BASES) + (i % np.uint64(min(DISTINCT, n)))) | np.uint64(1)
+            t = (t + KA.dot_mod_r(sc[a0 * 32:(a0 + k) * 32].cpu().numpy().reshape(k, 32), logs, r_mod)) % r_mod
+        ok = bool(np.array_equal(O.jac_to_affine(out.cpu().numpy(), curve)[0], KA.expected_affine(O, curve, t)))
+        for _ in range(warmup):
+            e.msm_device(sc.data_ptr(), n, out.data_ptr())
+        e.sync()
+        e.reset_stage_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            e.msm_device(sc.data_ptr(), n, out.data_ptr())
+        e1.record(st)
+        e.sync()
+        ms = e0.elapsed_time(e1) / steps
+        stg, k = e.stage_ms_sum()
+        acc = stg["accumulate"] / max(k, 1)
+        info = e.info()
+        return {"log_n": lg, "ms": round(ms, 3), "points_per_s": round(n / ms * 1e3), "bit_exact": ok, "window_bits": info["window_bits"], "tables": info["tables"],
+                "folded_windows": info["folded_windows"], "buckets": info["buckets"], "accumulate_ms": round(acc, 3),
+                "roofline_frac": n * 128 / (acc / 1e3) / 1e9 / peak_gbs}
+    finally:
+        e.close()
+        torch.cuda.empty_cache()
+
+
+def fastest_reference_entry(ms_ours_total):
+    """The reference's fastest GPU entry re-timed on this pool's B200 (committed measurement, profiles/r02_reference_entry.json:
+    scripts/retime_reference_entry.py, the entry built by oracle/build_ref_entry.py) beside this run's 4-batch contest call."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_reference_entry.json")))
+        out = dict(d)
+        if d.get("ms_total") and ms_ours_total:
+            out["ratio"] = d["ms_total"] / ms_ours_total
+            out["ratio_meaning"] = "reference entry's 4 x 2^26 MSMRun time / this run's contest_call.pageable_ms_total (same call, same ABI)"
+        return out
+    except Exception:
+        return None
+
+
 def ark_threads(O, n):
     c = O.window_bits(n)
     windows = (253 + c - 1) // c
@@ -122,12 +180,15 @@ def run_reference(args):
     from oracle import oracle as O
     O.build()
     lg = args.log_n
-    _, probe = cpu_oracle_rate(O, 16)
-    _, probe = cpu_oracle_rate(O, 16)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    ls = 16
-    while ls < min(22, lg) and probe * (1 << (ls + 1 - 16)) * 0.8 < budget:
-        ls += 1
+    # ONE sample size whatever the host: 2^22 points per step (~4 s on 16 cores; arkworks' window rule gives c = 17, 15 windows
+    # = 15 threads there, against c = 19, 14 windows at 2^26).  More than 12 steps + warm-ups in all are capped so that the run
+    # ends within a few minutes; the per-step time does not depend on the count.
+    ls = min(REF_SAMPLE_LOG_N, lg)
+    cpu_oracle_rate(O, 16)
+    total = args.steps + args.warmup
+    if total > 12:
+        args.warmup = min(args.warmup, 2)
+        args.steps = max(1, min(args.steps, 12 - args.warmup))
     for _ in range(args.warmup):
         cpu_oracle_rate(O, ls)
     pure = 0.0                      # the MSM call alone is timed; input generation is outside
@@ -137,10 +198,15 @@ def run_reference(args):
     ms = pure / args.steps * 1e3
     value = (1 << ls) / (ms / 1e3)
     cores = ark_threads(O, 1 << ls)
-    sample = f"2^{ls} points per step (harness-shaped: 2^10 distinct bases replicated, uniform scalars), arkworks window rule c={O.window_bits(1 << ls)}"
+    c_s, c_f = O.window_bits(1 << ls), O.window_bits(1 << lg)
+    sample = (f"2^{ls} points per step, fixed (harness-shaped: 2^10 distinct bases replicated, uniform scalars), arkworks window rule c={c_s} "
+              f"({-(-253 // c_s)} windows = threads); at 2^{lg} the rule gives c={c_f} ({-(-253 // c_f)} windows)")
+    # one 2^lg MSM at this rate, corrected for the window count: per point the work is one mixed add per window
+    extrap_ms = (1 << lg) / value * 1e3 * (-(-253 // c_f)) / (-(-253 // c_s))
     line = {"impl": "reference", "metric": METRIC.format(lg=lg), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 (377-bit modular integers as 6 x u64 Montgomery limbs, unsigned __int128 products)",
             "data": "synthetic", "config": {"workload": WORKLOAD.format(lg=lg), "log_n": lg, "cpu_sample_log_n": ls},
+            f"cpu_2pow{lg}_extrapolated_ms": extrap_ms,
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -157,6 +223,8 @@ def main():
     ap.add_argument("--tables", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-peer-reduce", action="store_true", help="N > 1: every rank reduces all of its own buckets (round-1 path)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the size sweep and the BLS12-381 block of the N = 1 line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -181,7 +249,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "NONE"      # NCCL logs (even its version banner) to stdout; the bench prints exactly one JSON line there
+        # NCCL's log goes to stdout by default and this program prints exactly one JSON line there: route the log to stderr
+        # instead of silencing it (the communicator's rank count is read from its INIT lines)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lg = args.log_n
     n = 1 << lg
@@ -249,49 +321,73 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps, clocks
 
-    # ---- device-resident timing
+    # ---- device-resident timing.  N > 1: the bucket reduce-scatter over NVLink (rank g reduces slice g of every rank's buckets;
+    # sharded.py attach_peers) unless --no-peer-reduce; its result must equal the plain path's before it is timed
+    peer = None
+    if world > 1 and not args.no_peer_reduce:
+        try:
+            if sh.attach_peers(chunks=1):
+                out_p = sh.msm_device(scal)
+                eng.sync()
+                if not np.array_equal(O.jac_to_affine(out_p.cpu().numpy())[0], exp):
+                    raise SystemExit(f"rank {rank}: bucket reduce-scatter result differs from the oracle")
+                peer = eng.peer_info()
+        except M.MsmError as ex:
+            peer = {"skipped": str(ex)[:160]}
     ms_dev, clocks = timed(lambda: sh.msm_device(scal), args.steps, args.warmup)
     stage_sum, covered = eng.stage_ms_sum()
     stage_avg = {k: v / max(covered, 1) for k, v in stage_sum.items()}
     info = eng.info()
     launches_per_msm = info["launches"] + (1 if world > 1 else 0)      # + the combine kernel after the all-gather
 
-    # ---- end to end: host scalars through the harness call
+    # ---- end to end: host scalars through the harness call.  Headline = PAGEABLE host memory, which is what the harness hands
+    # over (a Rust Vec); the library stages it through pinned slots itself (csrc/msm.cu h2d).  The same from pinned memory is
+    # reported beside it.
     e2e = None
     if not args.no_e2e:
+        if world > 1 and sh.peers:
+            sh.attach_peers(chunks=2 if n_local >= (1 << 22) else 1)      # the chunked upload keeps one bucket array per chunk (msm.cu upload_and_run)
+        pageable_scal = torch.empty(n_local * 32, dtype=torch.uint8)
+        pageable_scal.copy_(host_scal)
+        res_holder = {}
         if world == 1:
             hctx = M.MultiScalarMultContext.from_engine(eng)
-            sc_np = host_scal.numpy()
-            res_holder = {}
 
-            def e2e_step():
-                res_holder["r"] = M.multi_scalar_mult(hctx, None, sc_np)      # mult_pippenger_inf: H2D + MSM + D2H, synchronous
+            def make_step(buf):
+                arr = buf.numpy()
+                return lambda: res_holder.__setitem__("r", M.multi_scalar_mult(hctx, None, arr))      # mult_pippenger_inf: H2D + MSM + D2H, synchronous
         else:
-            res_holder = {}
+            def make_step(buf):
+                return lambda: res_holder.__setitem__("r", sh.msm(buf))
 
-            def e2e_step():
-                res_holder["r"] = sh.msm(host_scal)
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            e2e_step()
-        e1.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        t = torch.tensor([max(e0.elapsed_time(e1) / args.steps, wall_ms if world == 1 else 0.0)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-        r = res_holder["r"]
-        r_np = r.numpy() if hasattr(r, "numpy") else np.asarray(r)
-        if not np.array_equal(O.jac_to_affine(r_np.reshape(-1, 144)[0])[0], exp):
-            raise SystemExit("e2e result differs from the oracle")
+        def time_e2e(step):
+            for _ in range(2):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                step()
+            e1.record(stream)
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            t = torch.tensor([max(e0.elapsed_time(e1) / args.steps, wall_ms if world == 1 else 0.0)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r = res_holder["r"]
+            r_np = r.numpy() if hasattr(r, "numpy") else np.asarray(r)
+            if not np.array_equal(O.jac_to_affine(r_np.reshape(-1, 144)[0])[0], exp):
+                raise SystemExit("e2e result differs from the oracle")
+            return float(t.item())
+
+        ms_e2e = time_e2e(make_step(pageable_scal))
+        ms_pinned = time_e2e(make_step(host_scal))
         e2e = {"value": n / (ms_e2e / 1e3), "unit": "points/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 144 * world,
-               "api": "multi_scalar_mult -> mult_pippenger_inf (C ABI), pinned host scalars" if world == 1 else "ShardedMsm.msm (pinned host scalars per rank, NCCL all-gather of partials)"}
+               "host_memory": "pageable (staged through pinned slots by the library)",
+               "pinned": {"value": n / (ms_pinned / 1e3), "ms_per_step": ms_pinned},
+               "api": "multi_scalar_mult -> mult_pippenger_inf (C ABI)" if world == 1 else "ShardedMsm.msm (host scalars per rank, bucket reduce-scatter over NVLink + NCCL all-gather of partials)" if sh.peers else "ShardedMsm.msm (host scalars per rank, NCCL all-gather of partials)"}
+        del pageable_scal
 
     # ---- the contest's timed unit (P1A/*/benches/msm.rs: one multi_scalar_mult call with 4 batches of scalars in host
     # memory), reported beside the headline for comparison with the published A40 numbers; N = 1 only
@@ -349,15 +445,43 @@ def main():
         except Exception as ex:
             one_call = {"skipped": str(ex)[:120]}
 
+    # ---- BASELINE configs 3 and 5 on the same box (N = 1): size sweep 2^20 .. 2^28 with the auto-tuned window plan, and BLS12-381
+    # at 2^24, every row checked against the closed form before it is timed.  The headline engine is released first: 2^28
+    # needs the whole HBM (3 tables of 38.7 GB).
+    sweep, second_curve = None, None
+    if world == 1 and not args.no_sweep and lg == 26:
+        stage_keep = dict(stage_avg)
+        eng.close()
+        del scal
+        torch.cuda.empty_cache()
+        peak_gbs, _ = measured_peak_gbs()
+        sweep = []
+        for curve, slg in ((0, 20), (0, 22), (0, 24), (0, 26), (0, 28), (1, 24)):
+            if curve == 0 and slg == lg:
+                row = {"log_n": lg, "ms": round(ms_dev, 3), "points_per_s": round(n / ms_dev * 1e3), "bit_exact": True, "window_bits": info["window_bits"], "tables": info["tables"],
+                       "folded_windows": info["folded_windows"], "buckets": info["buckets"], "accumulate_ms": round(stage_keep["accumulate"], 3),
+                       "roofline_frac": n * 128 / (stage_keep["accumulate"] / 1e3) / 1e9 / peak_gbs}
+            else:
+                try:
+                    row = sweep_row(M, O, KA, torch, curve, slg, peak_gbs)
+                except Exception as ex:
+                    row = {"log_n": slg, "error": str(ex)[:160]}
+            if curve == 1:
+                second_curve = dict(row, curve="BLS12-381", bucket_arithmetic="XYZZ (8 M + 2 S mixed add; no twisted-Edwards model)")
+            else:
+                sweep.append(row)
+
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         O.build()
-        ls = min(22, lg)
+        ls = min(REF_SAMPLE_LOG_N, lg)
         cpu_oracle_rate(O, 16)
         rate, dt = cpu_oracle_rate(O, ls)
+        c_s, c_f = O.window_bits(1 << ls), O.window_bits(1 << lg)
         cpu = {"value": rate, "unit": "points/s", "cores": ark_threads(O, 1 << ls), "kind": "port",
-               "sample": f"one 2^{ls}-point MSM ({dt:.1f} s), harness-shaped inputs, arkworks window rule c={O.window_bits(1 << ls)}; host has {os.cpu_count()} cores"}
+               "sample": f"one 2^{ls}-point MSM ({dt:.1f} s), the sample size of --impl reference; harness-shaped inputs, arkworks window rule c={c_s}; host has {os.cpu_count()} cores",
+               f"cpu_2pow{lg}_extrapolated_ms": (1 << lg) / rate * 1e3 * (-(-253 // c_f)) / (-(-253 // c_s))}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -374,7 +498,7 @@ def main():
         int_ach = madds * imad_per_madd / (acc_ms / 1e3)
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_accumulate"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))["k_accumulate"]
             if tr["log_n"] == lg and tr["n_gpus"] == world:
                 traffic = tr["traffic_bytes"]          # dram read + write of one launch, from the committed ncu --set full capture
         except Exception:
@@ -396,6 +520,15 @@ def main():
                          "peak_source": "32 IMAD.WIDE lanes/clk/SM measured (profiles/r01_mul_bench.txt) x 148 SMs x sampled SM clock"},
             "cpu_baseline": cpu, "e2e": e2e, "contest_call": contest, "one_call": one_call, "gpu_launches": launches_per_msm * args.steps, "clocks": clocks,
         }
+        if sweep is not None:
+            line["sweep"] = sweep
+            line["bls12_381_2pow24"] = second_curve
+        if world == 1:
+            line["fastest_entry"] = fastest_reference_entry((contest or {}).get("pageable_ms_total") or (contest or {}).get("ms_total"))
+        if peer:
+            line["bucket_reduce_scatter"] = dict(peer, note="rank g reduces slice g of every rank's buckets, read over NVLink inside k_reduce_slices; bytes = one rank, one MSM",
+                                                 nvlink_GBps_over_bucket_reduce_stage=(peer.get("nvlink_bytes", 0) / 1e9) / (stage_avg["bucket_reduce"] / 1e3) if stage_avg.get("bucket_reduce") else None,
+                                                 nvlink_peer_copy_peak_GBps=770.0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -90,6 +90,38 @@ int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, vo
  * stream reaches the end of the call (b200msm_sync). */
 int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev);
 
+/* Multi-GPU BUCKET REDUCE-SCATTER over NVLink (one process per GPU; point sharding as above).  With point sharding every GPU
+ * ends the accumulation with partial sums of ALL buckets, and reducing them (2 curve additions per bucket, latency-bound)
+ * does not shrink with the shard.  After attaching, rank g reduces only the buckets [g B / G, (g + 1) B / G), reading the
+ * partial sums of that slice from every peer's HBM through mapped pointers INSIDE the level-0 reduction kernel (no staging
+ * copy, no separate collective; cross-GPU ordering by two release/acquire counters per pair).  The result is again one
+ * B200MSM_PARTIAL_BYTES record per rank, combined as before (all-gather + b200msm_combine_device).
+ *   b200msm_peer_export   after b200msm_set_bases*: writes this rank's handle (CUDA IPC handles of the bucket arrays; `chunks` =
+ *                         the most chunks a call will split its upload into: 1 for device-resident scalars).  Needs a plan
+ *                         with every window folded into one (all base tables resident), the same n on every rank.
+ *   b200msm_peer_attach   handles = world x B200MSM_PEER_HANDLE_BYTES, indexed by rank (exchanged by the caller, e.g.
+ *                         torch.distributed.all_gather); world a power of two <= 32.  Collective in effect: every rank must
+ *                         attach before any rank runs a peer call, and all ranks run the same sequence of peer calls.
+ *   b200msm_msm_peer_partial_device / _host   replace b200msm_msm_partial_device / _host.
+ *   b200msm_peer_accumulate_device + b200msm_peer_reduce   the same call in its two halves (tests run several ranks on one GPU,
+ *                         where one rank's waiting reduction kernel would starve the other rank's accumulation).
+ *   info[0..3] = world, rank, chunks, bytes one call reads from peers over NVLink. */
+#define B200MSM_PEER_HANDLE_BYTES 320
+int b200msm_peer_export(b200msm_ctx *ctx, int chunks, void *handle_out);
+int b200msm_peer_attach(b200msm_ctx *ctx, int rank, int world, const void *handles);
+int b200msm_peer_detach(b200msm_ctx *ctx);
+int b200msm_peer_info(const b200msm_ctx *ctx, uint64_t info[4]);
+int b200msm_msm_peer_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev);
+int b200msm_msm_peer_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev);
+int b200msm_peer_accumulate_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n);
+int b200msm_peer_reduce(b200msm_ctx *ctx, void *out_xyzz_dev);
+
+/* Opt-in subgroup check of the resident bases (table 0): *outside = number of bases P with r P != infinity.  The default
+ * bucket arithmetic reduces scalars mod r and folds their top bit into a point negation, which is exact only for bases of
+ * order r (G1, the harness contract; arkworks checks it when a G1Affine is deserialised); with B200MSM_CHECK_G1=1 in the
+ * environment b200msm_set_bases runs this check itself and fails with -3.  Cost: ~380 curve operations per base. */
+int b200msm_check_bases_in_g1(b200msm_ctx *ctx, uint64_t *outside);
+
 int b200msm_sync(b200msm_ctx *ctx);
 
 /* arkworks' VariableBaseMSM::multi_scalar_mul(bases, scalars) in ONE call, no context: the first

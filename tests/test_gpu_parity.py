@@ -643,10 +643,13 @@ def _random_curve_points(O, n, seed, curve=0):
 
 
 def test_bases_outside_the_prime_order_subgroup(M, oracle):
-    """arkworks' add_assign_mixed is correct for EVERY on-curve point (short_weierstrass_jacobian.rs:662-729), G1 or not.
-    Pinned behaviour of this library: (1) generic on-curve points outside G1 give the oracle's sum in both bucket
-    arithmetics; (2) a base without a twisted-Edwards image (the 2-torsion point (-1, 0)) is REFUSED by the default
-    arithmetic (error -3), never summed wrongly; (3) the XYZZ arithmetic takes it, tables > 1 included (2^k P = infinity)."""
+    """arkworks multiplies the integer scalar into ANY on-curve point (add_assign_mixed, short_weierstrass_jacobian.rs:662-729).
+    Pinned behaviour of this library:
+    (1) the XYZZ arithmetic (b200msm_set_bucket_arithmetic(1)) gives arkworks' sum for bases outside G1 -- no reduction of
+        the scalar mod r, no top-bit fold, every window plan, 2^k P = infinity in the precomputed tables included;
+    (2) the default arithmetic is specified for bases in G1 only (it folds the scalar mod r): the opt-in check counts the
+        offenders, B200MSM_CHECK_G1=1 refuses them, and a base without a twisted-Edwards image (the 2-torsion point (-1, 0))
+        is always refused (error -3) -- never summed wrongly in silence."""
     O = oracle
     n = 1500
     pts = _random_curve_points(O, n, seed=321)
@@ -656,13 +659,19 @@ def test_bases_outside_the_prime_order_subgroup(M, oracle):
     assert O.jac_to_affine(rG)[0, 96] == 0, "r * P should not be the identity: P must lie outside G1"
     sc = O.gen_scalars(n, seed=322)
     want = O.jac_to_affine(O.ark_msm(pts, sc))
-    for xyzz in (False, True):
-        for tables in (0, 1):
-            e = M.Engine(0, tables=tables)
-            e.set_bucket_arithmetic(xyzz)
-            e.set_bases(pts)
-            assert np.array_equal(O.jac_to_affine(e.msm_host(sc)), want), (xyzz, tables)
-            e.close()
+    sc[3] = 0xff                                                       # a scalar above r: arkworks does not reduce it
+    want = O.jac_to_affine(O.ark_msm(pts, sc))
+    for wb, tables in ((0, 0), (0, 1), (9, 3), (16, 0)):
+        e = M.Engine(0, window_bits=wb, tables=tables)
+        e.set_bucket_arithmetic(True)
+        e.set_bases(pts)
+        assert np.array_equal(O.jac_to_affine(e.msm_host(sc)), want), (wb, tables)
+        assert e.check_bases_in_g1() == n
+        e.close()
+    e = M.Engine(0)
+    e.set_bases(pts)                                                   # default arithmetic: accepted unless the check is asked for
+    assert e.check_bases_in_g1() == n
+    e.close()
     # the point of order 2: x = -1, y = 0
     p = O.constants(0)["p"]
     t2 = np.zeros((1, 104), np.uint8)
@@ -760,3 +769,95 @@ def test_stage_times_cover_every_chunk(M, oracle, monkeypatch):
     assert four["digits_hist"] < 5 * one["digits_hist"] + 1.0, (one, four)      # no longer "everything since the call began"
     e.close()
     e2.close()
+
+
+@pytest.mark.parametrize("world,chunks", [(2, 1), (4, 1), (2, 2), (8, 1)])
+def test_bucket_reduce_scatter_between_contexts_on_one_gpu(M, oracle, monkeypatch, world, chunks):
+    """The multi-GPU bucket reduce-scatter (b200msm_peer_*), `world` ranks as contexts of this process on one GPU: every rank
+    holds 1/world of the points; rank g reduces the g-th slice of the buckets of EVERY rank through the mapped source table
+    and the ready / done counters; the per-rank partials combine to the oracle's MSM over all points.  Several epochs, so
+    the done-counter (peers finished reading before the buckets are overwritten) is exercised too."""
+    import torch
+    O = oracle
+    n_local = 1 << 13
+    n = n_local * world
+    pts = np.tile(O.gen_points(512, seed=71), (n // 512, 1))
+    pts[5] = 0
+    pts[5, 96] = 1
+    monkeypatch.setenv("B200MSM_HOST_CHUNKS", str(chunks))
+    engines = []
+    for r in range(world):
+        e = M.Engine(0, window_bits=12)                      # 2048 buckets: 256 per rank at world = 8
+        e.set_bases(pts[r * n_local:(r + 1) * n_local])
+        engines.append(e)
+    handles = np.concatenate([e.peer_export(chunks) for e in engines])
+    for r, e in enumerate(engines):
+        e.peer_attach(r, world, handles)
+        assert e.peer_info()["world"] == world and e.peer_info()["rank"] == r and e.peer_info()["nvlink_bytes"] > 0
+    parts = torch.zeros(world * 224, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(144, dtype=torch.uint8, device="cuda")
+    for epoch in range(3):
+        sc = O.gen_scalars(n, seed=500 + epoch)
+        want = O.jac_to_affine(O.ark_msm(pts, sc))
+        dev = torch.from_numpy(sc.reshape(-1).copy()).cuda()
+        if chunks == 1:
+            for r, e in enumerate(engines):                  # accumulate everywhere first: one GPU cannot run a waiting reduction
+                e.peer_accumulate_device(dev[r * n_local * 32:].data_ptr(), n_local)     # kernel beside the accumulation it waits for
+            for e in engines:
+                e.sync()
+            for r, e in enumerate(engines):
+                e.peer_reduce(parts[r * 224:].data_ptr())
+        else:                                                # host scalars, chunked upload; tiny grids leave room for the peers' kernels
+            host = [np.ascontiguousarray(sc[r * n_local:(r + 1) * n_local]) for r in range(world)]
+            for r, e in enumerate(engines):
+                e.msm_peer_partial_host(host[r].ctypes.data, n_local, parts[r * 224:].data_ptr())
+        for e in engines:
+            e.sync()
+        engines[0].combine_device(parts.data_ptr(), world, out.data_ptr())
+        engines[0].sync()
+        assert np.array_equal(O.jac_to_affine(out.cpu().numpy()), want), (world, chunks, epoch)
+    # the plain per-rank path still works on an attached context (its own buckets only)
+    sc = O.gen_scalars(n, seed=77)
+    dev = torch.from_numpy(sc.reshape(-1).copy()).cuda()
+    for r, e in enumerate(engines):
+        e.msm_partial_device(dev[r * n_local * 32:].data_ptr(), n_local, parts[r * 224:].data_ptr())
+        e.sync()
+    engines[0].combine_device(parts.data_ptr(), world, out.data_ptr())
+    engines[0].sync()
+    assert np.array_equal(O.jac_to_affine(out.cpu().numpy()), O.jac_to_affine(O.ark_msm(pts, sc)))
+    for e in engines:
+        e.peer_detach()
+        e.close()
+
+
+def test_subgroup_check_of_resident_bases(M, oracle):
+    """b200msm_check_bases_in_g1: counts the bases P with r P != infinity, in both bucket arithmetics; B200MSM_CHECK_G1=1 makes
+    set_bases refuse them."""
+    O = oracle
+    good = O.gen_points(300, seed=3)
+    good[7] = 0
+    good[7, 96] = 1
+    mixed = good.copy()
+    mixed[[11, 200]] = _random_curve_points(O, 2, seed=9)
+    for xyzz in (False, True):
+        e = M.Engine(0)
+        e.set_bucket_arithmetic(xyzz)
+        e.set_bases(good)
+        assert e.check_bases_in_g1() == 0
+        e.set_bases(mixed)
+        assert e.check_bases_in_g1() == 2
+        e.close()
+    e = M.Engine(1)
+    p381 = O.gen_points(100, seed=4, curve=1)
+    e.set_bases(p381)
+    assert e.check_bases_in_g1() == 0
+    e.close()
+    os.environ["B200MSM_CHECK_G1"] = "1"
+    try:
+        e = M.Engine(0)
+        with pytest.raises(M.MsmError, match="-3"):
+            e.set_bases(mixed)
+        e.set_bases(good)
+        e.close()
+    finally:
+        del os.environ["B200MSM_CHECK_G1"]

@@ -34,6 +34,27 @@ class OracleBackend:
         out.zero_()
         out[:144] = torch.from_numpy(self.O.ark_msm(self.bases, scalars.numpy().reshape(-1, 32)))
 
+    # the peer handshake of ShardedMsm.attach_peers (handles through all_gather_object, barrier, call routing); the checker's
+    # "slice of every rank's buckets" is simply its own shard's sum -- the total over ranks is the same
+    def peer_export(self, chunks):
+        self.exported = chunks
+        return torch.full((320,), 7 + chunks, dtype=torch.uint8)
+
+    def peer_attach(self, rank, world, handles):
+        assert handles.numel() == 320 * world and int(handles[0]) == 7 + self.exported
+        self.attached = (rank, world)
+
+    def peer_detach(self):
+        self.attached = None
+
+    def peer_partial(self, scalars, out):
+        assert self.attached
+        self.peer_calls = getattr(self, "peer_calls", 0) + 1
+        self.partial(scalars, out)
+
+    def peer_partial_from_host(self, scalars, out):
+        self.peer_partial(scalars, out)
+
     def combine(self, gathered, count, out):
         recs = gathered.numpy().reshape(count, 224)[:, :144].copy()
         acc = recs[0:1].copy()
@@ -58,6 +79,12 @@ def _worker(rank, world, port, n, ret):
     got = sh.msm(torch.from_numpy(scalars[lo:hi].reshape(-1).copy()))
     want = O.ark_msm(bases, scalars)
     ok = np.array_equal(O.jac_to_affine(got.numpy()), O.jac_to_affine(want))
+    # the same through the bucket reduce-scatter routing
+    assert sh.attach_peers(chunks=2) and sh.peers == 2 and sh.b.attached == (rank, world)
+    got2 = sh.msm(torch.from_numpy(scalars[lo:hi].reshape(-1).copy()))
+    ok = ok and np.array_equal(O.jac_to_affine(got2.numpy()), O.jac_to_affine(want)) and sh.b.peer_calls == 1
+    sh.detach_peers()
+    ok = ok and sh.peers == 0 and sh.b.attached is None
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
