@@ -50,15 +50,21 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// 16-byte loads that bypass the non-coherent path: the record may live in a peer GPU's memory and was written during this launch's wait
-__device__ __forceinline__ void load_xyzz_cv(xyzz_t &d, const xyzz_t *src) {
+// peer = true: 16-byte loads that fetch again (ld.global.cv): the record lives in a peer GPU's memory and was written while
+// this launch was already waiting; peer = false: this GPU's own data, complete before the launch -- ordinary cached loads
+__device__ __forceinline__ void load_xyzz_src(xyzz_t &d, const xyzz_t *src, bool peer) {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
     uint4 *t = reinterpret_cast<uint4 *>(&d);
+    if (peer) {
 #pragma unroll
-    for (int i = 0; i < XYZZ_VEC; i++) t[i] = __ldcv(s + i);
+        for (int i = 0; i < XYZZ_VEC; i++) t[i] = __ldcv(s + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < XYZZ_VEC; i++) t[i] = s[i];
+    }
 }
 template <class C, bool INDIRECT>
-__global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict__ in, const red_src_t *__restrict__ srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t m,
+__global__ void __launch_bounds__(128, 3) k_reduce_slices(const xyzz_t *__restrict__ in, const red_src_t *__restrict__ srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t m,
                                                        xyzz_t *__restrict__ outS, xyzz_t *__restrict__ outT,
                                                        const uint32_t *__restrict__ wait_flags, uint32_t wait_n, uint32_t epoch) {
     __shared__ xyzz_t sh[64];
@@ -79,7 +85,8 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
         if (INDIRECT) {        // a bucket = the sum of its pieces, over every chunk the point set was accumulated in, on every GPU
             for (uint32_t ch = 0; ch < nsrc; ch++) {
                 const uint32_t *po = srcs[ch].poff;
-                const uint32_t p0 = __ldcv(po + k), p1 = __ldcv(po + k + 1);
+                const bool peer = wait_flags != nullptr;
+                const uint32_t p0 = peer ? __ldcv(po + k) : po[k], p1 = peer ? __ldcv(po + k + 1) : po[k + 1];
                 const xyzz_t *src = srcs[ch].res;
                 bool big = (blockDim.x & 31) == 0 && p1 - p0 > BIG_BUCKET_PIECES;            // whole warps only
                 uint32_t todo = __ballot_sync(0xffffffffu, big);
@@ -99,14 +106,14 @@ __global__ void __launch_bounds__(128) k_reduce_slices(const xyzz_t *__restrict_
                     const uint32_t q0 = __shfl_sync(0xffffffffu, p0, owner), q1 = __shfl_sync(0xffffffffu, p1, owner);
                     xyzz_t part;
                     Grp<C>::set_inf(part);
-                    for (uint32_t q = q0 + lane; q < q1; q += 32) { load_xyzz_cv(b, src + q); Grp<C>::add_ni(part, b); }
+                    for (uint32_t q = q0 + lane; q < q1; q += 32) { load_xyzz_src(b, src + q, peer); Grp<C>::add_ni(part, b); }
                     warp_sum<C>(part, shw[warp]);
                     if (lane == 0) store_xyzz(&shw[warp][16], part);
                     __syncwarp();
                     if ((int)lane == owner) { load_xyzz(b, &shw[warp][16]); Grp<C>::add_ni(run, b); }
                     __syncwarp();
                 }
-                if (!big) for (uint32_t q = p0; q < p1; q++) { load_xyzz_cv(b, src + q); Grp<C>::add_ni(run, b); }
+                if (!big) for (uint32_t q = p0; q < p1; q++) { load_xyzz_src(b, src + q, peer); Grp<C>::add_ni(run, b); }
             }
         } else {
             load_xyzz(b, in + k);

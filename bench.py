@@ -112,6 +112,7 @@ def cpu_oracle_rate(O, log_sample, threads=None):
 
 def sweep_row(M, O, KA, torch, curve, lg, peak_gbs, warmup=2, steps=3):
     """One size of the sweep: fresh engine, generated bases (2^15 distinct, replicated), closed-form check, CUDA-event timing."""
+    import numpy as np
     n = 1 << lg
     e = M.Engine(curve)
     try:
@@ -251,9 +252,12 @@ def main():
     if world > 1:
         # NCCL's log goes to stdout by default and this program prints exactly one JSON line there: route the log to stderr
         # instead of silencing it (the communicator's rank count is read from its INIT lines)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (at level VERSION / WARN, which this image presets, NCCL printf()s a bare version banner to stdout; at INFO the banner
+        # is a log line like the rest.)  An environment that already chose a log file is left alone.
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lg = args.log_n
     n = 1 << lg
