@@ -99,6 +99,16 @@ struct Bls12_377 {
         constexpr uint32_t v[14] = {0xcfd10d5u, 0x9457a38u, 0x383e475u, 0x7e96cb8u, 0x388e8d9u, 0xd00b5abu, 0xd32ebe1u, 0x0c15e03u, 0x5ac3c51u, 0xa270ad8u, 0xe68d2ebu, 0xbe54908u, 0x8029609u, 0x00001c4u};
         return v[i];
     }
+    // Table entries of the integer accumulate path hold x 2^406 (the Montgomery form of fp29.cuh); plain numbers for the
+    // conversions on the cold side:  mul(x 2^392, 2^406) = x 2^406,  mul(x 2^406, 2^378) = x 2^392.
+    FP_HD static constexpr uint32_t te_c406(int i) {
+        constexpr uint32_t v[14] = {0x9eaf730u, 0xe3ffffdu, 0x5c533e2u, 0x2718ec3u, 0xb6e2622u, 0xf5a2c7eu, 0x51ba717u, 0xb6edf83u, 0x9cbdd85u, 0xf055f3bu, 0x47628eau, 0xe55b0efu, 0x2a14aabu, 0x0001574u};
+        return v[i];
+    }
+    FP_HD static constexpr uint32_t te_c378(int i) {
+        constexpr uint32_t v[14] = {0xffffffeu, 0xee7ffffu, 0xffffef5u, 0x45779ffu, 0xfffd1e9u, 0xa08bed6u, 0x1c2193bu, 0xfe15d8eu, 0xbba4c19u, 0xbd6d89cu, 0x9f47f26u, 0xde2a738u, 0xb73d075u, 0x0000a38u};
+        return v[i];
+    }
 };
 
 // BLS12-377 with short-Weierstrass XYZZ buckets instead of the twisted-Edwards ones: the same field and curve, the group
@@ -145,6 +155,8 @@ struct Bls12_381 {
     FP_HD static constexpr uint32_t te_s(int) { return 0; }
     FP_HD static constexpr uint32_t te_s3(int) { return 0; }
     FP_HD static constexpr uint32_t te_cy(int) { return 0; }
+    FP_HD static constexpr uint32_t te_c406(int) { return 0; }
+    FP_HD static constexpr uint32_t te_c378(int) { return 0; }
     FP_HD static constexpr uint32_t r(int i) {
         constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
         return v[i];

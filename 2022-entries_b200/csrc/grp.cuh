@@ -78,15 +78,22 @@ template <class C> struct GrpTe {
         TeD<C>::madd(acc, q);
     }
     __device__ __noinline__ static void acc_export(xyzz_t &out, const acc_t &a) { TeD<C>::to_int(out, a); }
-    __device__ __forceinline__ static void madd_staged(xyzz_t &acc, const uint4 *st, int stride, bool negate) {
-        te_entry_t e;
-        uint4 *t = reinterpret_cast<uint4 *>(&e);
+    // acc (cold representation) += staged entry THROUGH THE HOT ARITHMETIC (fp29.cuh, Te29::madd): the group-law test kernel
+    // exercises exactly what k_accumulate runs; conversions in and out cost 8 multiplies, irrelevant there
+    __device__ __noinline__ static void madd_staged(xyzz_t &acc, const uint4 *st, int stride, bool negate) {
+        te29_t a;
+        Te29::import_from(a, acc);
+        fp29 v[3];
 #pragma unroll
-        for (int k = 0; k < ENTRY_VEC; k++) t[k] = st[k * stride];
-        te_pre_t q;
-        Te<C>::unpack(q, e);
-        if (negate) Te<C>::negate(q);
-        Te<C>::madd(acc, q);
+        for (int k = 0; k < 3; k++) {
+            fp_abi t;
+            const uint4 v0 = st[(3 * k) * stride], v1 = st[(3 * k + 1) * stride], v2 = st[(3 * k + 2) * stride];
+            t.w[0] = v0.x; t.w[1] = v0.y; t.w[2] = v0.z; t.w[3] = v0.w; t.w[4] = v1.x; t.w[5] = v1.y; t.w[6] = v1.z; t.w[7] = v1.w;
+            t.w[8] = v2.x; t.w[9] = v2.y; t.w[10] = v2.z; t.w[11] = v2.w;
+            Fp29::repack_from_abi(v[k], t);
+        }
+        Te29::madd(a, v[0], v[1], v[2], negate);
+        Te29::export_to(acc, a);
     }
     __device__ __noinline__ static void add_ni(xyzz_t &a, const xyzz_t &b) { Te<C>::add(a, b); }
     __device__ __noinline__ static void dbl_ni(xyzz_t &a) { Te<C>::dbl(a); }
@@ -188,6 +195,23 @@ template <class G> struct AccNative {          // the group's own integer arithm
     __device__ __forceinline__ static void init(acc_t &a) { G::set_inf(a); }
     __device__ __forceinline__ static void madd_staged(acc_t &acc, const uint4 *st, int stride, bool negate) { G::madd_staged(acc, st, stride, negate); }
     __device__ __forceinline__ static void export_to(xyzz_t &out, const acc_t &a) { out = a; }
+};
+template <class C> struct AccTe29 {            // twisted Edwards in the 13 x 29-bit field (fp29.cuh): the default on BLS12-377
+    typedef te29_t acc_t;
+    __device__ __forceinline__ static void init(acc_t &a) { Te29::set_inf(a); }
+    __device__ __forceinline__ static void unpack3(fp29 &r, const uint4 *st, int stride) {
+        fp_abi t;
+        const uint4 v0 = st[0], v1 = st[stride], v2 = st[2 * stride];
+        t.w[0] = v0.x; t.w[1] = v0.y; t.w[2] = v0.z; t.w[3] = v0.w; t.w[4] = v1.x; t.w[5] = v1.y; t.w[6] = v1.z; t.w[7] = v1.w;
+        t.w[8] = v2.x; t.w[9] = v2.y; t.w[10] = v2.z; t.w[11] = v2.w;
+        Fp29::repack_from_abi(r, t);
+    }
+    __device__ __forceinline__ static void madd_staged(acc_t &acc, const uint4 *st, int stride, bool negate) {
+        fp29 ymx, ypx, kt;
+        unpack3(ymx, st, stride); unpack3(ypx, st + 3 * stride, stride); unpack3(kt, st + 6 * stride, stride);
+        Te29::madd(acc, ymx, ypx, kt, negate);
+    }
+    __device__ __forceinline__ static void export_to(xyzz_t &out, const acc_t &a) { Te29::export_to(out, a); }
 };
 template <class C> struct AccFp64Te {          // twisted Edwards on the FP64 pipe
     typedef GrpTe<C> G;

@@ -124,6 +124,67 @@ __global__ void __launch_bounds__(128, 3) k_reduce_slices(const xyzz_t *__restri
     block_tree_sum<C>(tot, sh);
     if (threadIdx.x == 0) store_xyzz(outT + blockIdx.x, tot);
 }
+// Multi-GPU bucket reduce-scatter, the exchange itself: merged[k - bucket_base] = sum over the nsrc sources (every GPU's chunks;
+// srcs[0] is this GPU's own) of bucket k, for the PEER_TPB consecutive buckets of this block.  A block pulls each source's
+// PEER_TPB records (28 KB, contiguous whenever every bucket of the range is one piece -- always with uniform scalars) with
+// coalesced 16-byte cp.async from the peer's HBM over NVLink into shared memory, double-buffered: the copy of source s + 1
+// is in flight while the threads add source s, so the NVLink time hides behind the curve additions of the 3 resident blocks.
+// (Reading the records thread by thread, as the single-GPU level 0 does, moved 16 bytes per NVLink request and took 7.5 ms
+// for 0.85 GB at 8 GPUs: profiles/r02_peer_reduce.txt.)  Buckets split into several pieces take the per-thread path.
+#define PEER_TPB 128
+template <class C>
+__global__ void __launch_bounds__(PEER_TPB, 3) k_peer_merge(const red_src_t *__restrict__ srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t nslice,
+                                                            xyzz_t *__restrict__ merged, const uint32_t *__restrict__ wait_flags, uint32_t wait_n, uint32_t epoch) {
+    extern __shared__ uint4 sm_peer[];                       // [2][XYZZ_VEC][PEER_TPB]
+    __shared__ uint32_t first_piece[2], fast[2];
+    if (threadIdx.x < wait_n)                                // the peers' bucket sums of this epoch must be complete
+        while ((int32_t)(ld_acquire_sys(wait_flags + threadIdx.x) - epoch) < 0) __nanosleep(100);
+    __syncthreads();
+    const uint32_t b0 = blockIdx.x * PEER_TPB;               // first bucket of the block within the slice
+    const uint32_t cnt = nslice - b0 < PEER_TPB ? nslice - b0 : PEER_TPB;
+    const uint32_t k0 = bucket_base + b0, k = k0 + threadIdx.x;
+    auto issue = [&](uint32_t s) {                           // start the copy of source s into buffer s & 1
+        const uint32_t buf = s & 1;
+        if (threadIdx.x == 0) {
+            const uint32_t pf = __ldcv(srcs[s].poff + k0), pl = __ldcv(srcs[s].poff + k0 + cnt);
+            first_piece[buf] = pf;
+            fast[buf] = (pl - pf == cnt) ? 1u : 0u;          // every bucket has at least one piece: cnt pieces <=> one each
+        }
+        __syncthreads();
+        if (fast[buf]) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(srcs[s].res + first_piece[buf]);
+            uint4 *dst = sm_peer + buf * (XYZZ_VEC * PEER_TPB);
+            for (uint32_t g = threadIdx.x; g < cnt * XYZZ_VEC; g += PEER_TPB) {
+                const uint32_t r = g / XYZZ_VEC, v = g - r * XYZZ_VEC;
+                cp_async16(dst + v * PEER_TPB + r, src + g);
+            }
+        }
+        cp_async_commit();
+    };
+    xyzz_t acc, b;
+    Grp<C>::set_inf(acc);
+    issue(0);
+    for (uint32_t s = 0; s < nsrc; s++) {
+        if (s + 1 < nsrc) issue(s + 1); else cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint32_t buf = s & 1;
+        if (threadIdx.x < cnt) {
+            if (fast[buf]) {
+                const uint4 *src = sm_peer + buf * (XYZZ_VEC * PEER_TPB) + threadIdx.x;
+                uint4 *t = reinterpret_cast<uint4 *>(&b);
+#pragma unroll
+                for (int v = 0; v < XYZZ_VEC; v++) t[v] = src[v * PEER_TPB];
+                Grp<C>::add_ni(acc, b);
+            } else {
+                const uint32_t p0 = __ldcv(srcs[s].poff + k), p1 = __ldcv(srcs[s].poff + k + 1);
+                for (uint32_t q = p0; q < p1; q++) { load_xyzz_src(b, srcs[s].res + q, true); Grp<C>::add_ni(acc, b); }
+            }
+        }
+        __syncthreads();                                     // the buffer is refilled two sources later
+    }
+    if (threadIdx.x < cnt) store_xyzz(merged + b0 + threadIdx.x, acc);
+}
 // out[g] = sum of in[g*group .. (g+1)*group)   (one block per group)
 template <class C>
 __global__ void __launch_bounds__(128) k_block_sum(const xyzz_t *__restrict__ in, uint32_t group, xyzz_t *__restrict__ out) {

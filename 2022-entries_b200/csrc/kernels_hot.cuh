@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(ACC_TPB, ACC_MINB) k_accumulate(const typename
     const uint32_t piece = order[j];
     const uint32_t start = piece_start[piece], len = piece_len[piece];
     if constexpr (FP64 && C::HAS_TE) accumulate_piece<C, AccFp64Te<C>>(tables, refs, start, len, stage, res + piece);
+    else if constexpr (C::HAS_TE) accumulate_piece<C, AccTe29<C>>(tables, refs, start, len, stage, res + piece);      // 13 x 29-bit field (fp29.cuh)
     else accumulate_piece<C, AccNative<G>>(tables, refs, start, len, stage, res + piece);
 }
 

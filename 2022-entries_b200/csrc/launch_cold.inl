@@ -11,6 +11,14 @@ void LaunchCold<C>::reduce_slices(cudaStream_t st, const xyzz_t *in, const red_s
     else k_reduce_slices<C, false><<<n_out / block, block, 0, st>>>(in, nullptr, 0, 0, m, outS, outT, nullptr, 0, 0);
 }
 
+template <class C>
+void LaunchCold<C>::peer_merge(cudaStream_t st, const red_src_t *srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t nslice, xyzz_t *merged,
+                               const uint32_t *wait_flags, uint32_t wait_n, uint32_t epoch) {
+    constexpr int smem = 2 * XYZZ_VEC * PEER_TPB * 16;
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(k_peer_merge<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
+    k_peer_merge<C><<<cdiv(nslice, PEER_TPB), PEER_TPB, smem, st>>>(srcs, nsrc, bucket_base, nslice, merged, wait_flags, wait_n, epoch);
+}
 template <class C> void LaunchCold<C>::block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out) {
     k_block_sum<C><<<ngroups, group < 128 ? group : 128, 0, st>>>(in, group, out);
 }

@@ -106,6 +106,7 @@ struct b200msm_ctx {
         void *mapped[PEER_MAX][3] = {};      // cudaIpcOpenMemHandle results to close again
         red_src_t *src_tab = nullptr;        // device: world x chunks sources
         xyzz_t *red_buf = nullptr;
+        xyzz_t *merged = nullptr;            // this rank's slice of the buckets, summed over every GPU (k_peer_merge)
         std::vector<red_step_t> steps;
         fin_args_t fin;
         uint64_t nvlink_bytes = 0;           // bytes one level-0 launch reads from peers (algorithmic)
@@ -128,9 +129,9 @@ struct b200msm_ctx {
     }
     void peer_release() {
         for (auto &m : peer.mapped) for (void *&q : m) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-        void *ptrs[] = {peer.flags, peer.flag_ptrs, peer.src_tab, peer.red_buf};
+        void *ptrs[] = {peer.flags, peer.flag_ptrs, peer.src_tab, peer.red_buf, peer.merged};
         for (void *q : ptrs) if (q) cudaFree(q);
-        peer.flags = nullptr; peer.flag_ptrs = nullptr; peer.src_tab = nullptr; peer.red_buf = nullptr;
+        peer.flags = nullptr; peer.flag_ptrs = nullptr; peer.src_tab = nullptr; peer.red_buf = nullptr; peer.merged = nullptr;
         peer.world = 0; peer.epoch = 0; peer.steps.clear();
     }
     void free_plan() {
@@ -540,11 +541,12 @@ template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *
         if (s.kind == 2) LaunchCold<C>::block_sum(st, s.in, s.n_out, s.m, s.outS);
         else if (s.kind == 1) LaunchCold<C>::reduce_slices(st, s.in, nullptr, 0, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
         else if (!peer) LaunchCold<C>::reduce_slices(st, nullptr, ctx->src_tab, (uint32_t)nchunks, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
-        else {
-            LaunchCold<C>::reduce_slices(st, nullptr, P.src_tab, (uint32_t)(P.world * P.chunks), (uint32_t)P.rank * (ctx->nbuckets / (uint32_t)P.world), s.n_out, s.block, s.m,
-                                         s.outS, s.outT, P.flags, (uint32_t)P.world, P.epoch);
+        else {              // the exchange (k_peer_merge reads the peers over NVLink), `done` to the peers, then the ordinary level 0 on the merged slice
+            const uint32_t nslice = ctx->nbuckets / (uint32_t)P.world;
+            LaunchCold<C>::peer_merge(st, P.src_tab, (uint32_t)(P.world * P.chunks), (uint32_t)P.rank * nslice, nslice, P.merged, P.flags, (uint32_t)P.world, P.epoch);
             k_peer_signal<<<1, PEER_MAX, 0, st>>>(P.flag_ptrs, (uint32_t)P.world, PEER_MAX + (uint32_t)P.rank, P.epoch);      // done reading
-            launches++;
+            LaunchCold<C>::reduce_slices(st, P.merged, nullptr, 0, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
+            launches += 2;
         }
         launches++;
     }
@@ -892,6 +894,7 @@ int b200msm_peer_attach(b200msm_ctx *ctx, int rank, int world, const void *handl
     CK(cudaMemcpy(P.flag_ptrs, fl, sizeof(uint32_t *) * world, cudaMemcpyHostToDevice));
     P.rank = rank; P.world = world; P.epoch = 0;
     rc = make_red_plan(ctx, (uint32_t)world, (uint32_t)rank, &P.red_buf, P.steps, P.fin); if (rc) { P.world = 0; return rc; }
+    CK(dmalloc(&P.merged, (size_t)ctx->nbuckets / world));
     P.nvlink_bytes = (uint64_t)(world - 1) * (ctx->nbuckets / (uint32_t)world) * (uint64_t)P.chunks * (sizeof(xyzz_t) + 8);
     return 0;
 }

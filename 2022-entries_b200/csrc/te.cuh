@@ -22,12 +22,13 @@
 #pragma once
 #include "ec.cuh"
 #include "fpd.cuh"
+#include "fp29.cuh"
 
 namespace b200msm {
 
 struct te_entry_t { uint32_t w[36]; };       // (y - x, y + x, 2 d x y), each a canonical value bit-packed 12 x 32.  Montgomery
-                                             // form: 2^392 for the integer accumulator (default: unpacking is bit slicing),
-                                             // 2^384 (arkworks') when the context runs the FP64-pipe accumulator
+                                             // form: 2^406 for the integer accumulator (fp29.cuh: unpacking in the hot loop is
+                                             // bit slicing), 2^384 (arkworks') when the context runs the FP64-pipe accumulator
 struct te_pre_t { fp ymx, ypx, kt; };        // the same in registers
 
 template <class C> struct Te {
@@ -37,25 +38,39 @@ template <class C> struct Te {
     FP_HD static void load_const(fp &r, int which) {
 #pragma unroll
         for (int i = 0; i < FP_LIMBS; i++)
-            r.l[i] = which == 0 ? C::te_k(i) : which == 1 ? C::te_f(i) : which == 2 ? C::te_s(i) : which == 3 ? C::te_s3(i) : C::te_cy(i);
+            r.l[i] = which == 0 ? C::te_k(i) : which == 1 ? C::te_f(i) : which == 2 ? C::te_s(i) : which == 3 ? C::te_s3(i) : which == 4 ? C::te_cy(i)
+                   : which == 5 ? C::te_c406(i) : C::te_c378(i);
     }
     FP_HD static void set_inf(xyzz_t &a) { F::set_zero(a.x); F::set_one(a.y); F::set_one(a.zz); F::set_zero(a.zzz); }
     // the neutral element is the only point of G1 with X = 0
     FP_HD static bool is_inf(const xyzz_t &a) { return F::is_zero(a.x); }
 
-    // ark = false: entries hold 2^392-form values (bit slicing only); ark = true: arkworks form (one multiply each)
+    // The cold kernels' view of an entry (this file's 14 x 28 arithmetic, Montgomery 2^392): one multiply per value either
+    // way -- ark = false: the entry holds 2^406-form values (the hot loop's form); ark = true: arkworks form (2^384)
     FP_HD static void unpack_one(fp &r, const uint32_t *w, bool ark) {
         fp_abi t;
 #pragma unroll
         for (int i = 0; i < 12; i++) t.w[i] = w[i];
-        if (ark) F::from_abi(r, t); else F::repack_from_abi(r, t);
+        if (ark) { F::from_abi(r, t); return; }
+        fp v, c;
+        F::repack_from_abi(v, t);
+        load_const(c, 6);
+        F::mul(r, v, c);                          // x 2^406 * 2^378 / 2^392 = x 2^392
     }
     FP_HD static void unpack(te_pre_t &q, const te_entry_t &e, bool ark = false) {
         unpack_one(q.ymx, e.w, ark); unpack_one(q.ypx, e.w + 12, ark); unpack_one(q.kt, e.w + 24, ark);
     }
     FP_HD static void pack_one(uint32_t *w, fp v, bool ark) {
         fp_abi t;
-        if (ark) F::to_abi(t, v); else { F::reduce(v); F::repack_to_abi(t, v); }
+        if (ark) F::to_abi(t, v);
+        else {
+            fp c;
+            load_const(c, 5);
+            F::norm(v);
+            F::mul(v, v, c);                      // x 2^392 * 2^406 / 2^392 = x 2^406
+            F::csub_p(v);
+            F::repack_to_abi(t, v);
+        }
 #pragma unroll
         for (int i = 0; i < 12; i++) w[i] = t.w[i];
     }
@@ -207,6 +222,63 @@ template <class C> struct Te {
         F::set_zero(a.zzz);                       // T is not needed by to_sw_affine
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// The accumulate kernel's mixed addition in the 13 x 29-bit field (fp29.cuh): the same add-2008-hwcd-3, every operand
+// normalised (value bounds in units of p beside each line; the top limb takes up to 9p).
+struct te29_t { fp29 x, y, z, t; };
+
+#if defined(__CUDACC__) && defined(EC_MUL_BY_CALL)
+template <class C> __device__ __noinline__ fp29 fp29_mul_call(fp29 a, fp29 b) { fp29 r; Fp29::mul(r, a, b); return r; }
+#endif
+
+template <class C> struct Te29T {       // a template only so that its host / device members are instantiated where they are used
+    typedef Fp29 F;
+#if defined(__CUDACC__) && defined(EC_MUL_BY_CALL)
+    __device__ __forceinline__ static void M(fp29 &r, const fp29 &a, const fp29 &b) { r = fp29_mul_call<C>(a, b); }
+#else
+    FP_HD static void M(fp29 &r, const fp29 &a, const fp29 &b) { F::mul(r, a, b); }
+#endif
+    FP_HD static void set_inf(te29_t &a) { F::set_zero(a.x); F::set_one(a.y); F::set_one(a.z); F::set_zero(a.t); }
+    // ymx, ypx, kt: the three entry values (2^406 form, canonical); negate: -(x, y) = (-x, y)
+    FP_HD static void madd(te29_t &acc, const fp29 &ymx, const fp29 &ypx, const fp29 &kt_in, bool negate) {
+        fp29 a, b, c, d, e, f, g, h, kt;
+        if (negate) F::template neg<2>(kt, kt_in); else kt = kt_in;     //              2
+        F::template sub<3>(a, acc.y, acc.x);      // Y1 - X1                    5
+        M(a, a, negate ? ypx : ymx);              // A                          1.1
+        F::add(b, acc.y, acc.x);                  // Y1 + X1                    2.2
+        M(b, b, negate ? ymx : ypx);              // B
+        M(c, acc.t, kt);                          // C = T1 * 2 d t2
+        F::add(d, acc.z, acc.z);                  // D = 2 Z1                   2.2
+        F::template sub<3>(e, b, a);              // E = B - A                  4.1
+        F::template sub<3>(f, d, c);              // F = D - C                  5.2
+        F::add(g, d, c);                          // G = D + C                  3.3
+        F::add(h, b, a);                          // H = B + A                  2.2
+        M(acc.x, e, f);                           // X3 = E F
+        M(acc.y, g, h);                           // Y3 = G H
+        M(acc.t, e, h);                           // T3 = E H
+        M(acc.z, f, g);                           // Z3 = F G
+    }
+    // bucket sum -> the representation of the reduction kernels (14 x 28, 2^392): one multiply per coordinate
+    FP_HD static void export_to(xyzz_t &out, const te29_t &a) {
+        F::to_fp28(out.x, a.x); F::to_fp28(out.y, a.y); F::to_fp28(out.zz, a.z); F::to_fp28(out.zzz, a.t);
+    }
+    // the reverse (tests: continue an accumulation held in the cold representation)
+    FP_HD static void import_from(te29_t &a, const xyzz_t &in) {
+        fp c, v;
+        Te<C>::load_const(c, 5);
+        const fp *src[4] = {&in.x, &in.y, &in.zz, &in.zzz};
+        fp29 *dst[4] = {&a.x, &a.y, &a.z, &a.t};
+        for (int k = 0; k < 4; k++) {
+            v = *src[k];
+            Fp<C>::norm(v);
+            Fp<C>::mul(v, v, c);
+            Fp<C>::csub_p(v);
+            F::repack_from_fp28(*dst[k], v);
+        }
+    }
+};
+typedef Te29T<Bls12_377> Te29;
 
 // ---------------------------------------------------------------------------------------------
 // The same mixed addition on the FP64 pipe (fpd.cuh: 8 x 48-bit limbs in doubles, R = 2^384): the accumulate kernel's

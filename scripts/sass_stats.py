@@ -1,10 +1,11 @@
 """Static SASS statistics of k_accumulate<Bls12_377, false> in an object / library: instruction histogram of the accumulate loop
 (the span of the last backward branch) and of the multiplier subroutine it calls, per mixed add.
-  python scripts/sass_stats.py <file.o|.so> [--dump]"""
+  python scripts/sass_stats.py <file.o|.so> [kernel-name-fragment] [--dump]"""
 import collections, re, subprocess, sys
 path = sys.argv[1]
 txt = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
-m = re.search(r"Function : (\S*k_accumulateINS_9Bls12_377ELb0\S*)(.*?)(?=\n\s*Function :|\Z)", txt, re.S)
+pat = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "k_accumulateINS_9Bls12_377ELb0"
+m = re.search(r"Function : (\S*" + pat + r"\S*)(.*?)(?=\n\s*Function :|\Z)", txt, re.S)
 body = m.group(2)
 ins = [(int(a, 16), re.sub(r"^@!?U?P\w+\s+", "", t.strip())) for a, t in re.findall(r"/\*([0-9a-f]{4,})\*/\s+([^;]+);", body)]
 back = [(a, int(re.search(r"0x([0-9a-f]+)", t).group(1), 16)) for a, t in ins if t.startswith("BRA") and re.search(r"0x([0-9a-f]+)", t) and int(re.search(r"0x([0-9a-f]+)", t).group(1), 16) < a]

@@ -119,7 +119,60 @@ template <class C> static void fp_mul_raw(const uint32_t *a, const uint32_t *b, 
         for (int j = 0; j < FP_LIMBS; j++) r[i * FP_LIMBS + j] = t.l[j];
     }
 }
+// the 13 x 29-bit field of the accumulate kernel (csrc/fp29.cuh): raw multiply, and the twisted-Edwards mixed add Te29::madd
+// driven like te_ops (op 0: a + reps*b, op 3: a - reps*b), entries built and packed exactly as the table builder does
+static void fp29_mul_raw(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        fp29 x, y, t;
+        for (int j = 0; j < F29_LIMBS; j++) { x.l[j] = a[i * F29_LIMBS + j]; y.l[j] = b[i * F29_LIMBS + j]; }
+        Fp29::mul(t, x, y);
+        for (int j = 0; j < F29_LIMBS; j++) r[i * F29_LIMBS + j] = t.l[j];
+    }
+}
+static void te29_ops(int op, const affine_abi_t *a, const affine_abi_t *b, uint32_t *out, size_t n, int reps) {
+    typedef Bls12_377 C; typedef Fp<C> F; typedef Te<C> T;
+    for (size_t i = 0; i < n; i++) {
+        te_entry_t ent[2];
+        for (int k = 0; k < 2; k++) {
+            const affine_abi_t &s = k == 0 ? a[i] : b[i];
+            fp x, y, nu, nv, dv, den, inv;
+            F::from_abi(x, s.x); F::from_abi(y, s.y);
+            T::map_prepare(nu, nv, dv, den, x, y);
+            F::inv(inv, den);
+            T::map_finish(ent[k], nu, nv, dv, y, inv);
+        }
+        fp29 v[2][3];
+        for (int k = 0; k < 2; k++) for (int c = 0; c < 3; c++) {
+            fp_abi t;
+            for (int w = 0; w < 12; w++) t.w[w] = ent[k].w[12 * c + w];
+            Fp29::repack_from_abi(v[k][c], t);
+        }
+        te29_t acc;
+        Te29::set_inf(acc);
+        Te29::madd(acc, v[0][0], v[0][1], v[0][2], false);
+        for (int k = 0; k < reps; k++) Te29::madd(acc, v[1][0], v[1][1], v[1][2], op == 3);
+        xyzz_t q;
+        Te29::export_to(q, acc);
+        te29_t back;                                 // round trip of the representation change
+        Te29::import_from(back, q);
+        Te29::export_to(q, back);
+        fp x, y;
+        bool finite = T::to_sw_affine(x, y, q);
+        if (!finite) { F::set_zero(x); F::set_one(y); }
+        fp_abi ox, oy; F::to_abi(ox, x); F::to_abi(oy, y);
+        for (int k = 0; k < 12; k++) { out[i * 26 + k] = ox.w[k]; out[i * 26 + 12 + k] = oy.w[k]; }
+        out[i * 26 + 24] = finite ? 0 : 1; out[i * 26 + 25] = 0;
+    }
+}
 extern "C" {
+int emul_fp29_mul_raw(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) { fp29_mul_raw(a, b, r, n); return 0; }
+int emul_te29_op(int op, const void *a, const void *b, void *out, size_t n, int reps) { te29_ops(op, (const affine_abi_t *)a, (const affine_abi_t *)b, (uint32_t *)out, n, reps); return 0; }
+int emul_fp29_constants(uint32_t *out) {
+    for (int i = 0; i < F29_LIMBS; i++) { out[i] = P377x29::p(i); out[13 + i] = P377x29::one(i); out[26 + i] = P377x29::to392(i); }
+    for (int k = 0; k < 8; k++) for (int i = 0; i < F29_LIMBS; i++) out[39 + k * 13 + i] = kp_dom29(k + 1, i);
+    for (int i = 0; i < FP_LIMBS; i++) { out[160 + i] = Bls12_377::te_c406(i); out[174 + i] = Bls12_377::te_c378(i); }
+    return 0;
+}
 int emul_fp_mul_raw(int curve, const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n) {
     if (curve == 0) fp_mul_raw<Bls12_377>(a, b, r, n); else fp_mul_raw<Bls12_381>(a, b, r, n);
     return 0;

@@ -798,6 +798,8 @@ def test_bucket_reduce_scatter_between_contexts_on_one_gpu(M, oracle, monkeypatc
     out = torch.zeros(144, dtype=torch.uint8, device="cuda")
     for epoch in range(3):
         sc = O.gen_scalars(n, seed=500 + epoch)
+        if epoch == 2:
+            sc[:] = sc[0]                                    # one giant bucket per window, split into pieces: the per-thread path of k_peer_merge
         want = O.jac_to_affine(O.ark_msm(pts, sc))
         dev = torch.from_numpy(sc.reshape(-1).copy()).cuda()
         if chunks == 1:

@@ -20,7 +20,7 @@ HERE = os.path.join(ROOT, "tests", "host_emul")
 def _build_emul(name, flags):
     so = os.path.join(HERE, name)
     src = os.path.join(HERE, "emul.cpp")
-    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "ec.cuh", "te.cuh")]
+    hdrs = [os.path.join(ROOT, "2022-entries_b200", "csrc", h) for h in ("fp.cuh", "fp29.cuh", "ec.cuh", "te.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-x", "c++"] + flags + [src, "-o", so])
     return so
@@ -42,6 +42,9 @@ def emul(request):
     so = _build_emul("emul.so", _hot_flags()) if request.param == "hot" else _build_emul("emul_plain.so", [])
     L = ctypes.CDLL(so)
     L.emul_fp_mul_raw.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.emul_fp29_mul_raw.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.emul_te29_op.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    L.emul_fp29_constants.argtypes = [ctypes.c_void_p]
     vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     L.emul_fp_op.argtypes = [i32, i32, vp, vp, vp, sz]
     L.emul_ec_op.argtypes = [i32, i32, vp, vp, sz, i32]
@@ -148,6 +151,75 @@ def test_multiplier_accepts_unnormalised_limbs(emul, la, lb):
         assert all(int(R[i, j]) < (1 << 28) for j in range(13)), "result not normalised"
         assert vr % p == va * vb * rinv % p
         assert vr < va * vb // (1 << 392) + p + 1
+
+
+def test_fp29_constants(emul):
+    """csrc/fp29.cuh tables (13 x 29-bit limbs, R = 2^406) and the conversion constants of fp.cuh, re-derived from p."""
+    p = RB.CURVES[0]["p"]
+    out = np.zeros(192, np.uint32)
+    emul.emul_fp29_constants(_p(out))
+    val = lambda off, n=13, bits=29: sum(int(out[off + i]) << (bits * i) for i in range(n))
+    assert val(0) == p and all(int(out[i]) < (1 << 29) for i in range(13))
+    assert val(13) == pow(2, 406, p) and val(26) == pow(2, 392, p)
+    assert (-pow(p, -1, 1 << 29)) % (1 << 29) == (1 << 29) - 1 and p % (1 << 29) == 1
+    for k in range(8):                                   # K p in limb-dominant form: same value, every low limb >= 2^29 - 1
+        assert val(39 + 13 * k) == (k + 1) * p
+        assert all(int(out[39 + 13 * k + i]) >= (1 << 29) - 1 for i in range(12))
+    assert val(160, 14, 28) == pow(2, 406, p) and val(174, 14, 28) == pow(2, 378, p)
+
+
+def test_fp29_multiplier(emul):
+    """Fp29::mul = a b / 2^406 mod p on normalised operands up to the largest representatives the mixed add forms (7p x 6p:
+    the top limb takes the excess), worst-case limbs included: no 64-bit column overflows, result normalised and < 1.1 p."""
+    rng = np.random.default_rng(29)
+    p = RB.CURVES[0]["p"]
+    n = 256
+    def rand_rep(k):                                     # a representative of a random residue below k p, as 13 x 29 limbs
+        v = int.from_bytes(rng.bytes(48), "little") % p + int(rng.integers(0, k)) * p
+        return v
+    A = np.zeros((n, 13), np.uint32); B = np.zeros((n, 13), np.uint32)
+    va, vb = [], []
+    for i in range(n):
+        a, b = rand_rep(7), rand_rep(6)
+        if i == 0:
+            a, b = 7 * p - 1, 6 * p - 1
+        if i == 1:                                       # every low limb at its maximum
+            a = ((7 * p) >> 348 << 348) - 1
+            b = ((6 * p) >> 348 << 348) - 1
+        va.append(a); vb.append(b)
+        for j in range(13):
+            A[i, j] = (a >> (29 * j)) & ((1 << 29) - 1) if j < 12 else a >> 348
+            B[i, j] = (b >> (29 * j)) & ((1 << 29) - 1) if j < 12 else b >> 348
+    R = np.zeros((n, 13), np.uint32)
+    emul.emul_fp29_mul_raw(_p(A), _p(B), _p(R), n)
+    rinv = pow(1 << 406, -1, p)
+    for i in range(n):
+        vr = sum(int(R[i, j]) << (29 * j) for j in range(13))
+        assert all(int(R[i, j]) < (1 << 29) for j in range(12))
+        assert vr % p == va[i] * vb[i] * rinv % p
+        assert vr < p + p // 10
+
+
+def test_te29_group_law(emul, oracle):
+    """Te29::madd (the accumulate kernel's mixed add, 13 x 29-bit field, entries in 2^406 form) == the oracle's Jacobian
+    arithmetic: P + Q chains, P + P, P - P through the neutral element, negated entries; representation round trip."""
+    O = oracle
+    n = 48
+    A, B = O.gen_points(n, seed=15), O.gen_points(n, seed=19)
+    B[0] = A[0]
+    B[1] = O.aff_neg(A[1:2])[0]
+    a96, b96 = np.ascontiguousarray(A[:, :96]), np.ascontiguousarray(B[:, :96])
+    out = np.zeros((n, 104), np.uint8)
+    jacA = _jac_from_aff(O, A, 0)
+    for op, reps in ((0, 1), (0, 7), (3, 1), (3, 5), (0, 0)):
+        emul.emul_te29_op(op, _p(a96), _p(b96), _p(out), n, reps)
+        j = jacA.copy()
+        for _ in range(reps):
+            j = O.jac_add_mixed(j, B if op == 0 else O.aff_neg(B))
+        want = O.jac_to_affine(j)
+        assert np.array_equal(out[:, 96], want[:, 96]), (op, reps)
+        fin = want[:, 96] == 0
+        assert np.array_equal(out[fin, :96], want[fin, :96]), (op, reps)
 
 
 def _xyzz_from_aff(O, aff, curve):
