@@ -360,9 +360,9 @@ class Engine:
         self._ck(lib().b200msm_peer_detach(self.h), "peer_detach")
 
     def peer_info(self):
-        a = (ctypes.c_uint64 * 4)()
+        a = (ctypes.c_uint64 * 6)()
         lib().b200msm_peer_info(self.h, a)
-        return dict(zip(("world", "rank", "chunks", "nvlink_bytes"), [int(v) for v in a]))
+        return dict(zip(("world", "rank", "chunks", "nvlink_bytes", "last_wait_us", "last_exchange_us"), [int(v) for v in a]))
 
     def msm_peer_partial_device(self, scalars_dev_ptr, n, out_xyzz_dev_ptr):
         self._ck(lib().b200msm_msm_peer_partial_device(self.h, ctypes.c_void_p(scalars_dev_ptr), n, ctypes.c_void_p(out_xyzz_dev_ptr)), "msm_peer_partial_device")

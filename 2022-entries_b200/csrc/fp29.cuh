@@ -118,6 +118,64 @@ struct Fp29 {
         sb[H - 1] = b.l[N - 1];
 #pragma unroll
         for (int k = 0; k < T; k++) t[k] = 0;
+#if defined(F29_K2)
+        // second Karatsuba level on z0 (6 = 3 + 3: 27 products instead of 36) and z2 (7 = 3 + 4, the top limb alone again:
+        // 41 instead of 49); the middle product stays schoolbook (its operands are already sums: a third sum would overflow)
+        {
+            uint32_t ua[3], ub[3];
+            uint64_t pm[5];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { ua[i] = a.l[i] + a.l[3 + i]; ub[i] = b.l[i] + b.l[3 + i]; }
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    if (i == 0 || j == 2) { t[i + j] = (uint64_t)a.l[i] * b.l[j]; t[6 + i + j] = (uint64_t)a.l[3 + i] * b.l[3 + j]; pm[i + j] = (uint64_t)ua[i] * ub[j]; }
+                    else { t[i + j] += (uint64_t)a.l[i] * b.l[j]; t[6 + i + j] += (uint64_t)a.l[3 + i] * b.l[3 + j]; pm[i + j] += (uint64_t)ua[i] * ub[j]; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) pm[k] -= t[k] + t[6 + k];
+#pragma unroll
+            for (int k = 0; k < 5; k++) t[3 + k] += pm[k];
+        }
+        {
+            uint32_t ua[4], ub[4];
+            uint64_t q0[5], qm[7];
+            uint64_t *u = t + 2 * L;                        // z2 columns 0..12 live in t[12..24]
+#pragma unroll
+            for (int i = 0; i < 3; i++) { ua[i] = a.l[L + i] + a.l[L + 3 + i]; ub[i] = b.l[L + i] + b.l[L + 3 + i]; }
+            ua[3] = a.l[N - 1];
+            ub[3] = b.l[N - 1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (i < 3 && j < 3) {
+                        if (i == 0 || j == 2) q0[i + j] = (uint64_t)a.l[L + i] * b.l[L + j];
+                        else q0[i + j] += (uint64_t)a.l[L + i] * b.l[L + j];
+                    }
+                    if (i == 0 || j == 3) { u[6 + i + j] = (uint64_t)a.l[L + 3 + i] * b.l[L + 3 + j]; qm[i + j] = (uint64_t)ua[i] * ub[j]; }
+                    else { u[6 + i + j] += (uint64_t)a.l[L + 3 + i] * b.l[L + 3 + j]; qm[i + j] += (uint64_t)ua[i] * ub[j]; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 7; k++) qm[k] -= (k < 5 ? q0[k] : 0) + u[6 + k];
+#pragma unroll
+            for (int k = 0; k < 5; k++) u[k] = q0[k];
+            u[5] = 0;
+#pragma unroll
+            for (int k = 0; k < 7; k++) u[3 + k] += qm[k];
+        }
+#pragma unroll
+        for (int i = 0; i < H; i++) {
+#pragma unroll
+            for (int j = 0; j < H; j++) {
+                if (i == 0 || j == H - 1) mid[i + j] = (uint64_t)sa[i] * sb[j];
+                else mid[i + j] += (uint64_t)sa[i] * sb[j];
+            }
+        }
+#else
 #pragma unroll
         for (int i = 0; i < H; i++) {
 #pragma unroll
@@ -135,6 +193,7 @@ struct Fp29 {
                 }
             }
         }
+#endif
         // z1 = mid - z0 - z2 per column (z0 has columns 0..10, z2 and mid 0..12), added at column offset 6
 #pragma unroll
         for (int k = 0; k < 2 * H - 1; k++) mid[k] -= (k < 2 * L - 1 ? t[k] : 0) + t[2 * L + k];

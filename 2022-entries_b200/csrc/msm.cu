@@ -110,6 +110,7 @@ struct b200msm_ctx {
         std::vector<red_step_t> steps;
         fin_args_t fin;
         uint64_t nvlink_bytes = 0;           // bytes one level-0 launch reads from peers (algorithmic)
+        cudaEvent_t ev[3] = {};              // last MSM: before the wait for the peers' `ready`, after it, after k_peer_merge
     } peer;
     // Stage boundaries: one event set per CHUNK (stages 0-3: digits, scatter, pieces, accumulate); the set of an MSM's
     // last chunk also takes the reduction and finalize boundaries (ev_last = 6) and closes the MSM.  A plain MSM is one set.
@@ -133,6 +134,7 @@ struct b200msm_ctx {
         for (void *q : ptrs) if (q) cudaFree(q);
         peer.flags = nullptr; peer.flag_ptrs = nullptr; peer.src_tab = nullptr; peer.red_buf = nullptr; peer.merged = nullptr;
         peer.world = 0; peer.epoch = 0; peer.steps.clear();
+        for (auto &e : peer.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
     }
     void free_plan() {
         void *ptrs[] = {tables, infmask, bad, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
@@ -278,7 +280,9 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     CK(dmalloc(&ctx->part_xyzz, 1));
     // two-level scatter when the list array is far beyond L2: bins of <= 24 MB of list each, at most BIN_MAX bins
     ctx->nbins = 0;
-    uint64_t bin_min_bytes = 512ull << 20;
+    // from 256 MB of lists on.  Measured (profiles/r02_scaling.txt): 2^23 points, c = 23, 369 MB of lists (the 8-GPU shard of
+    // 2^26): direct scatter 3.42 ms, two-level 1.66 ms; 2^22 points, c = 20, 218 MB: direct 0.79 ms, two-level 1.25 ms
+    uint64_t bin_min_bytes = 256ull << 20;
     uint64_t bin_bytes = 24ull << 20;
     if (const char *e = getenv("B200MSM_BIN_MIN_MB")) bin_min_bytes = (uint64_t)atoll(e) << 20;      // tests: force the two-level path
     if (const char *e = getenv("B200MSM_BIN_KB")) { bin_bytes = (uint64_t)atoll(e) << 10; if (bin_bytes == 0) bin_bytes = 1024; }   // ... with many bins at small n
@@ -543,10 +547,16 @@ template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *
         else if (!peer) LaunchCold<C>::reduce_slices(st, nullptr, ctx->src_tab, (uint32_t)nchunks, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
         else {              // the exchange (k_peer_merge reads the peers over NVLink), `done` to the peers, then the ordinary level 0 on the merged slice
             const uint32_t nslice = ctx->nbuckets / (uint32_t)P.world;
+            // the wait for the slowest peer's accumulation gets a launch (and a pair of events) of its own, so that the time of
+            // the exchange kernel is transfer + additions only (b200msm_peer_info)
+            cudaEventRecord(P.ev[0], st);
+            k_peer_wait<<<1, PEER_MAX, 0, st>>>(P.flags, (uint32_t)P.world, P.epoch);
+            cudaEventRecord(P.ev[1], st);
             LaunchCold<C>::peer_merge(st, P.src_tab, (uint32_t)(P.world * P.chunks), (uint32_t)P.rank * nslice, nslice, P.merged, P.flags, (uint32_t)P.world, P.epoch);
+            cudaEventRecord(P.ev[2], st);
             k_peer_signal<<<1, PEER_MAX, 0, st>>>(P.flag_ptrs, (uint32_t)P.world, PEER_MAX + (uint32_t)P.rank, P.epoch);      // done reading
             LaunchCold<C>::reduce_slices(st, P.merged, nullptr, 0, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
-            launches += 2;
+            launches += 3;
         }
         launches++;
     }
@@ -893,6 +903,7 @@ int b200msm_peer_attach(b200msm_ctx *ctx, int rank, int world, const void *handl
     CK(cudaMemcpy(P.src_tab, src, sizeof(red_src_t) * world * P.chunks, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(P.flag_ptrs, fl, sizeof(uint32_t *) * world, cudaMemcpyHostToDevice));
     P.rank = rank; P.world = world; P.epoch = 0;
+    for (auto &e : P.ev) if (!e) CK(cudaEventCreate(&e));
     rc = make_red_plan(ctx, (uint32_t)world, (uint32_t)rank, &P.red_buf, P.steps, P.fin); if (rc) { P.world = 0; return rc; }
     CK(dmalloc(&P.merged, (size_t)ctx->nbuckets / world));
     P.nvlink_bytes = (uint64_t)(world - 1) * (ctx->nbuckets / (uint32_t)world) * (uint64_t)P.chunks * (sizeof(xyzz_t) + 8);
@@ -906,9 +917,17 @@ int b200msm_peer_detach(b200msm_ctx *ctx) {
     return 0;
 }
 
-int b200msm_peer_info(const b200msm_ctx *ctx, uint64_t info[4]) {
+int b200msm_peer_info(b200msm_ctx *ctx, uint64_t info[6]) {
     if (!ctx || !info) return -1;
     info[0] = (uint64_t)ctx->peer.world; info[1] = (uint64_t)ctx->peer.rank; info[2] = (uint64_t)ctx->peer.chunks; info[3] = ctx->peer.nvlink_bytes;
+    info[4] = info[5] = 0;
+    if (ctx->peer.world && ctx->peer.epoch && cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+        float w = 0.f, m = 0.f;
+        if (cudaEventElapsedTime(&w, ctx->peer.ev[0], ctx->peer.ev[1]) == cudaSuccess && cudaEventElapsedTime(&m, ctx->peer.ev[1], ctx->peer.ev[2]) == cudaSuccess) {
+            info[4] = (uint64_t)(w * 1000.f); info[5] = (uint64_t)(m * 1000.f);
+        }
+        cudaGetLastError();
+    }
     return 0;
 }
 

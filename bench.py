@@ -341,6 +341,8 @@ def main():
     ms_dev, clocks = timed(lambda: sh.msm_device(scal), args.steps, args.warmup)
     stage_sum, covered = eng.stage_ms_sum()
     stage_avg = {k: v / max(covered, 1) for k, v in stage_sum.items()}
+    if peer and "world" in peer:
+        peer = eng.peer_info()              # with the last timed MSM's wait / exchange times
     info = eng.info()
     launches_per_msm = info["launches"] + (1 if world > 1 else 0)      # + the combine kernel after the all-gather
 
@@ -496,11 +498,11 @@ def main():
         acc_ms = stage_avg["accumulate"]
         alg_bytes = n_local * 128
         achieved = alg_bytes / (acc_ms / 1e3) / 1e9
-        # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (twisted-Edwards unified add: 7 multiplies x 329) vs the
+        # integer-pipe view: mixed adds per launch x IMAD.WIDE per mixed add (twisted-Edwards unified add: 7 multiplies x 302) vs the
         # measured IMAD.WIDE.U32 rate: 32 lanes / clk / SM -- the fmaheavy pipe is 89 % busy when the multiplier
         # microbenchmark sustains 378 IMAD.WIDE per 13.2 SM-clocks (profiles/r01_mul_bench.txt)
         madds = info["windows"] * n_local
-        imad_per_madd = 7 * 329                  # one-level Karatsuba multiplier (fp.cuh)
+        imad_per_madd = 7 * 302                  # 13 x 29-bit limbs, one-level Karatsuba + 14 reduction rounds (fp29.cuh)
         sm_mhz = clocks["sm_mhz"] or 1965
         int_peak = 32.0 * 148 * sm_mhz * 1e6
         int_ach = madds * imad_per_madd / (acc_ms / 1e3)
@@ -514,7 +516,7 @@ def main():
         line = {
             "metric": METRIC.format(lg=lg), "value": n / (ms_dev / 1e3), "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32 (377-bit modular integers as 14 x 28-bit limbs, IMAD.WIDE into u64 columns)", "data": "synthetic",
+            "dtype": "u32 (377-bit modular integers: 13 x 29-bit limbs in the accumulate kernel, 14 x 28-bit elsewhere; IMAD.WIDE into u64 columns)", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(lg=lg),
                        "log_n": lg, "points_per_gpu": n_local, "parallelism": f"point-shard x{world}" if world > 1 else "single GPU",
                        "window_bits": info["window_bits"], "windows": info["windows"], "tables": info["tables"], "folded_windows": info["folded_windows"],
@@ -535,7 +537,7 @@ def main():
             line["fastest_entry"] = fastest_reference_entry((contest or {}).get("pageable_ms_total") or (contest or {}).get("ms_total"))
         if peer:
             line["bucket_reduce_scatter"] = dict(peer, note="rank g reduces slice g of every rank's buckets, read over NVLink inside k_reduce_slices; bytes = one rank, one MSM",
-                                                 nvlink_GBps_over_bucket_reduce_stage=(peer.get("nvlink_bytes", 0) / 1e9) / (stage_avg["bucket_reduce"] / 1e3) if stage_avg.get("bucket_reduce") else None,
+                                                 nvlink_GBps_in_exchange_kernel=(peer.get("nvlink_bytes", 0) / 1e9) / (peer["last_exchange_us"] / 1e6) if peer.get("last_exchange_us") else None,
                                                  nvlink_peer_copy_peak_GBps=770.0)
         print(json.dumps(line), flush=True)
     if world > 1:

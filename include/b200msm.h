@@ -105,12 +105,14 @@ int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_
  *   b200msm_msm_peer_partial_device / _host   replace b200msm_msm_partial_device / _host.
  *   b200msm_peer_accumulate_device + b200msm_peer_reduce   the same call in its two halves (tests run several ranks on one GPU,
  *                         where one rank's waiting reduction kernel would starve the other rank's accumulation).
- *   info[0..3] = world, rank, chunks, bytes one call reads from peers over NVLink. */
+ *   info[0..5] = world, rank, chunks, bytes one call reads from peers over NVLink, and of the last peer call (after a stream
+ *                synchronisation): microseconds this rank waited for the slowest peer's accumulation, microseconds of the exchange
+ *                kernel (NVLink reads + curve additions). */
 #define B200MSM_PEER_HANDLE_BYTES 320
 int b200msm_peer_export(b200msm_ctx *ctx, int chunks, void *handle_out);
 int b200msm_peer_attach(b200msm_ctx *ctx, int rank, int world, const void *handles);
 int b200msm_peer_detach(b200msm_ctx *ctx);
-int b200msm_peer_info(const b200msm_ctx *ctx, uint64_t info[4]);
+int b200msm_peer_info(b200msm_ctx *ctx, uint64_t info[6]);
 int b200msm_msm_peer_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev);
 int b200msm_msm_peer_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev);
 int b200msm_peer_accumulate_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n);
