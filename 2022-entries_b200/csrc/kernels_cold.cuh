@@ -125,57 +125,72 @@ __global__ void __launch_bounds__(128, 3) k_reduce_slices(const xyzz_t *__restri
     if (threadIdx.x == 0) store_xyzz(outT + blockIdx.x, tot);
 }
 // Multi-GPU bucket reduce-scatter, the exchange itself: merged[k - bucket_base] = sum over the nsrc sources (every GPU's chunks;
-// srcs[0] is this GPU's own) of bucket k, for the PEER_TPB consecutive buckets of this block.  A block pulls each source's
-// PEER_TPB records (28 KB, contiguous whenever every bucket of the range is one piece -- always with uniform scalars) with
-// coalesced 16-byte cp.async from the peer's HBM over NVLink into shared memory, double-buffered: the copy of source s + 1
-// is in flight while the threads add source s, so the NVLink time hides behind the curve additions of the 3 resident blocks.
-// (Reading the records thread by thread, as the single-GPU level 0 does, moved 16 bytes per NVLink request and took 7.5 ms
-// for 0.85 GB at 8 GPUs: profiles/r02_peer_reduce.txt.)  Buckets split into several pieces take the per-thread path.
+// srcs[0] is this GPU's own) of bucket k, for the PEER_TPB consecutive buckets of this block.  The PEER_TPB records of one
+// source are contiguous (28 KB) whenever every bucket of the range is one piece -- always with uniform scalars -- and are
+// pulled from the peer's HBM over NVLink by ONE TMA bulk copy (cp.async.bulk global -> shared, completion on an mbarrier)
+// into a double buffer: the copy of source s + 1 is in flight while the threads add source s.  What that buys over SM-issued
+// loads is the request size on the link (profiles/r02_peer_reduce.txt, 8 GPUs, 0.85 GB per rank): 16-byte loads per thread
+// 7.5 ms for the stage, coalesced 16-byte cp.async 4.9 ms for this kernel (175 GB/s), bulk copies: see there.
+// Buckets split into several pieces (skewed scalar sets) take the per-thread path.
 #define PEER_TPB 128
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 template <class C>
 __global__ void __launch_bounds__(PEER_TPB, 3) k_peer_merge(const red_src_t *__restrict__ srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t nslice,
                                                             xyzz_t *__restrict__ merged, const uint32_t *__restrict__ wait_flags, uint32_t wait_n, uint32_t epoch) {
-    extern __shared__ uint4 sm_peer[];                       // [2][XYZZ_VEC][PEER_TPB]
-    __shared__ uint32_t first_piece[2], fast[2];
+    extern __shared__ __align__(128) uint8_t sm_peer[];      // [2][PEER_TPB] records of 224 bytes, as they lie in the source
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t fast[2];
     if (threadIdx.x < wait_n)                                // the peers' bucket sums of this epoch must be complete
         while ((int32_t)(ld_acquire_sys(wait_flags + threadIdx.x) - epoch) < 0) __nanosleep(100);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const uint32_t b0 = blockIdx.x * PEER_TPB;               // first bucket of the block within the slice
     const uint32_t cnt = nslice - b0 < PEER_TPB ? nslice - b0 : PEER_TPB;
     const uint32_t k0 = bucket_base + b0, k = k0 + threadIdx.x;
-    auto issue = [&](uint32_t s) {                           // start the copy of source s into buffer s & 1
+    // thread 0 starts the copy of source s into buffer s & 1 (the buffer's previous readers have passed a __syncthreads)
+    auto issue = [&](uint32_t s) {
         const uint32_t buf = s & 1;
-        if (threadIdx.x == 0) {
-            const uint32_t pf = __ldcv(srcs[s].poff + k0), pl = __ldcv(srcs[s].poff + k0 + cnt);
-            first_piece[buf] = pf;
-            fast[buf] = (pl - pf == cnt) ? 1u : 0u;          // every bucket has at least one piece: cnt pieces <=> one each
+        const uint32_t pf = __ldcv(srcs[s].poff + k0), pl = __ldcv(srcs[s].poff + k0 + cnt);
+        const bool f = pl - pf == cnt;                       // every bucket has at least one piece: cnt pieces <=> one each
+        fast[buf] = f ? 1u : 0u;
+        if (f) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar[buf], cnt * (uint32_t)sizeof(xyzz_t));
+            bulk_g2s(sm_peer + (size_t)buf * PEER_TPB * sizeof(xyzz_t), srcs[s].res + pf, cnt * (uint32_t)sizeof(xyzz_t), &bar[buf]);
+        } else {
+            mbar_arrive(&bar[buf]);                          // nothing to wait for: the phase completes at once
         }
-        __syncthreads();
-        if (fast[buf]) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(srcs[s].res + first_piece[buf]);
-            uint4 *dst = sm_peer + buf * (XYZZ_VEC * PEER_TPB);
-            for (uint32_t g = threadIdx.x; g < cnt * XYZZ_VEC; g += PEER_TPB) {
-                const uint32_t r = g / XYZZ_VEC, v = g - r * XYZZ_VEC;
-                cp_async16(dst + v * PEER_TPB + r, src + g);
-            }
-        }
-        cp_async_commit();
     };
     xyzz_t acc, b;
     Grp<C>::set_inf(acc);
-    issue(0);
+    if (threadIdx.x == 0) issue(0);
     for (uint32_t s = 0; s < nsrc; s++) {
-        if (s + 1 < nsrc) issue(s + 1); else cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
+        if (threadIdx.x == 0 && s + 1 < nsrc) issue(s + 1);
         const uint32_t buf = s & 1;
+        mbar_wait(&bar[buf], (s >> 1) & 1);                  // the (s / 2)-th use of this buffer
+        __syncthreads();                                     // fast[buf] written by thread 0 before its arrive
         if (threadIdx.x < cnt) {
             if (fast[buf]) {
-                const uint4 *src = sm_peer + buf * (XYZZ_VEC * PEER_TPB) + threadIdx.x;
-                uint4 *t = reinterpret_cast<uint4 *>(&b);
-#pragma unroll
-                for (int v = 0; v < XYZZ_VEC; v++) t[v] = src[v * PEER_TPB];
-                Grp<C>::add_ni(acc, b);
+                load_xyzz(b, reinterpret_cast<const xyzz_t *>(sm_peer + (size_t)buf * PEER_TPB * sizeof(xyzz_t)) + threadIdx.x);
+                if (s == 0) acc = b; else Grp<C>::add_ni(acc, b);      // the first source is this GPU's own sum: nothing to add it to yet
             } else {
                 const uint32_t p0 = __ldcv(srcs[s].poff + k), p1 = __ldcv(srcs[s].poff + k + 1);
                 for (uint32_t q = p0; q < p1; q++) { load_xyzz_src(b, srcs[s].res + q, true); Grp<C>::add_ni(acc, b); }

@@ -14,7 +14,7 @@ void LaunchCold<C>::reduce_slices(cudaStream_t st, const xyzz_t *in, const red_s
 template <class C>
 void LaunchCold<C>::peer_merge(cudaStream_t st, const red_src_t *srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t nslice, xyzz_t *merged,
                                const uint32_t *wait_flags, uint32_t wait_n, uint32_t epoch) {
-    constexpr int smem = 2 * XYZZ_VEC * PEER_TPB * 16;
+    constexpr int smem = 2 * PEER_TPB * (int)sizeof(xyzz_t);
     static bool configured = false;
     if (!configured) { cudaFuncSetAttribute(k_peer_merge<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); configured = true; }
     k_peer_merge<C><<<cdiv(nslice, PEER_TPB), PEER_TPB, smem, st>>>(srcs, nsrc, bucket_base, nslice, merged, wait_flags, wait_n, epoch);

@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-8}
+run() { # name, flags
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 $2 > gpurun_out/bench_n${N}_$1.json 2> gpurun_out/bench_n${N}_$1.err
+  echo "== N=$N $1 rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_n${N}_$1.json").read().strip().splitlines()[-1])
+    print(d["ms_per_step"], d["stages_ms"], d.get("bucket_reduce_scatter"), {k:v for k,v in (d.get("e2e") or {}).items() if k in ("ms_per_step","pageable")})
+except Exception as ex:
+    print("no json:", ex)
+PY
+}
+run peer ""
+run nopeer "--no-peer-reduce --no-e2e"
