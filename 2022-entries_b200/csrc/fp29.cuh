@@ -50,7 +50,8 @@ struct P377x29 {
     }
 };
 
-// limb i of K p with limbs 0..11 each borrowing 2^29 from the limb above ("limb dominant", as fp.cuh kp_dom)
+// limb i of K p with limbs 0..11 each borrowing 2 * 2^29 from the limb above ("limb dominant", as fp.cuh kp_dom; twice the
+// borrow because the subtrahend's limbs may exceed 2^29 by a carry: see norm)
 FP_HD constexpr uint32_t kp_dom29(int k, int i) {
     uint64_t carry = 0;
     uint32_t limb = 0;
@@ -60,8 +61,8 @@ FP_HD constexpr uint32_t kp_dom29(int k, int i) {
         carry = t >> F29_BITS;
         if (j == F29_LIMBS - 1) limb = (uint32_t)t;
     }
-    if (i < F29_LIMBS - 1) limb += (1u << F29_BITS);
-    if (i > 0) limb -= 1;
+    if (i < F29_LIMBS - 1) limb += (2u << F29_BITS);
+    if (i > 0) limb -= 2;
     return limb;
 }
 
@@ -77,15 +78,29 @@ struct Fp29 {
 #pragma unroll
         for (int i = 0; i < N; i++) r.l[i] = P::one(i);
     }
+    // ONE parallel carry step instead of a 12-deep chain: every limb hands its excess over 29 bits to the next one at the
+    // same time.  Inputs have limbs below 2^32 - 8 (sums of two operands, or operand + K p - operand), so a carry is at most
+    // 7 and the result has limbs 0..11 below 2^29 + 8: "normalised" in this file means that, not < 2^29 -- the multiplier's
+    // column bound has the room (48 of 64 units used), and sub / neg borrow twice 2^29 per limb so that such a limb can be
+    // subtracted.  Depth 3 instead of 36 dependent instructions: the accumulate kernel spends its non-multiplier time in
+    // these chains while the multiply pipe waits (profiles/r02_accumulate_variants.txt).
     FP_HD static void norm(fp29 &a) {
+#if defined(F29_SERIAL_NORM)
         uint32_t c = 0;
 #pragma unroll
         for (int i = 0; i < N - 1; i++) {
-            uint32_t t = a.l[i] + c;           // limbs stay below 2^31 + 2^29 here, c < 2^3
+            uint32_t t = a.l[i] + c;
             a.l[i] = t & F29_MASK;
             c = t >> F29_BITS;
         }
         a.l[N - 1] += c;
+#else
+        uint32_t c[N - 1];
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) { c[i] = a.l[i] >> F29_BITS; a.l[i] &= F29_MASK; }
+#pragma unroll
+        for (int i = 1; i < N; i++) a.l[i] += c[i - 1];
+#endif
     }
     FP_HD static void add(fp29 &r, const fp29 &a, const fp29 &b) {
 #pragma unroll
