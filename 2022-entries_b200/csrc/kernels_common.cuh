@@ -191,6 +191,49 @@ __global__ void __launch_bounds__(BINSC_TPB) k_bin_scatter(const uint2 *__restri
     for (int k = 0; k < BINSC_EPT; k++) if (v[k].x != 0xffffffffu) refs[slot[k]] = v[k].y;
 }
 
+// The same second level without a global atomic per reference (stands in for yrrid's in-shared-memory second pass,
+// Partition4096.cu:352-433).  k_bin_scatter is bound by ~66 G global atomics-with-return per second (profiles/
+// r01_ncu_scatter.txt); here a block of 1024 threads takes a tile of 64 K consecutive pairs -- all of one bin, bar the rare
+// tile that straddles a boundary -- and a histogram of the bin's buckets in shared memory:
+//   pass A  count the tile's pairs per bucket (shared-memory atomics, no return value needed);
+//   reserve one global atomicAdd per bucket the tile touches (2 - 4 pairs each at 2^26 points) replaces the count by the first slot;
+//   pass B  re-read the tile (L2), slot = shared-memory atomicAdd on that entry, store the reference.
+// The lists a tile writes to are its bin's (<= 24 MB), and the ~150 tiles in flight span a handful of bins: L2-resident.
+#define BS2_TPB 1024
+#define BS2_TILE (64u * 1024u)     // measured at 2^26: 32 K 10.3 ms, 64 K 10.0, 128 K 10.5, 256 K 21.9 (the re-read falls out of L2)
+#define BS2_MAX_SHIFT 15            // 32768 buckets per bin = 128 KB of shared memory
+__global__ void __launch_bounds__(BS2_TPB) k_bin_scatter_tiled(const uint2 *__restrict__ staging, const uint32_t *__restrict__ bucket_off, uint32_t nbuckets,
+                                                               int bin_shift, uint32_t tile, uint32_t *__restrict__ cursor, uint32_t *__restrict__ refs) {
+    extern __shared__ uint32_t bs2_hist[];
+    const uint32_t total = bucket_off[nbuckets];
+    const uint64_t t0 = (uint64_t)blockIdx.x * tile;
+    if (t0 >= total) return;
+    const uint32_t t1 = total - t0 < tile ? total : (uint32_t)t0 + tile;
+    const uint32_t per_bin = 1u << bin_shift, mask = per_bin - 1;
+    uint32_t pos = (uint32_t)t0;
+    while (pos < t1) {
+        const uint32_t bin = staging[pos].x >> bin_shift;                       // the same word for every thread
+        const uint32_t first = bin << bin_shift, next = first + per_bin < nbuckets ? first + per_bin : nbuckets;
+        const uint32_t bin_end = bucket_off[next];                               // where this bin's pairs end in the staging array
+        const uint32_t end = bin_end < t1 ? bin_end : t1;
+        for (uint32_t b = threadIdx.x; b < per_bin; b += BS2_TPB) bs2_hist[b] = 0;
+        __syncthreads();
+        for (uint32_t i = pos + threadIdx.x; i < end; i += BS2_TPB) atomicAdd(&bs2_hist[staging[i].x & mask], 1u);
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < per_bin; b += BS2_TPB) {
+            const uint32_t c = bs2_hist[b];
+            if (c) bs2_hist[b] = atomicAdd(&cursor[first + b], c);
+        }
+        __syncthreads();
+        for (uint32_t i = pos + threadIdx.x; i < end; i += BS2_TPB) {
+            const uint2 v = __ldcs(staging + i);
+            refs[atomicAdd(&bs2_hist[v.x & mask], 1u)] = v.y;
+        }
+        __syncthreads();
+        pos = end;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // multi-GPU bucket reduce-scatter: the two cross-GPU counters (protocol at k_reduce_slices, kernels_cold.cuh)
 // slot = this GPU's rank: flags[slot] of every peer (peer_flags[p] = peer p's flag array, mapped) <- epoch

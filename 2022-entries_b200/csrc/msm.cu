@@ -77,6 +77,8 @@ struct b200msm_ctx {
     uint2 *staging = nullptr;
     int bin_shift = 0;
     uint32_t nbins = 0;
+    size_t bs2_smem = 0;                // dynamic shared memory k_bin_scatter_tiled has been configured for
+    bool scatter_atomic = false;        // B200MSM_SCATTER=atomic: the round-1 second level (one global atomic per reference)
     xyzz_t *res = nullptr, *red_buf = nullptr, *part_xyzz = nullptr;
     uint8_t *scal_buf[2] = {nullptr, nullptr};
     uint8_t *raw_buf[2] = {nullptr, nullptr};   // one-call form: arkworks records of one upload step, double-buffered
@@ -290,6 +292,7 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
         uint64_t want = (ctx->max_refs * 4 + bin_bytes - 1) / bin_bytes;               // bins needed
         int lg_nb = 0; while ((1ull << lg_nb) < nb) lg_nb++;
         int lg_bins = 0; while ((1ull << lg_bins) < want && lg_bins < 8) lg_bins++;
+        while (lg_nb - lg_bins > BS2_MAX_SHIFT && lg_bins < 8) lg_bins++;             // the tiled second level keeps one bin's counters in shared memory
         if (lg_bins > lg_nb) lg_bins = lg_nb;
         ctx->bin_shift = lg_nb - lg_bins;
         ctx->nbins = (uint32_t)((nb + (1u << ctx->bin_shift) - 1) >> ctx->bin_shift);
@@ -490,7 +493,15 @@ template <class C> static int run_chunk_t(b200msm_ctx *ctx, const void *scalars_
     if (ctx->nbins > 1) {
         k_bin_init<<<cdiv(ctx->nbins, 256), 256, 0, st>>>(ctx->bucket_off, nb, ctx->bin_shift, ctx->nbins, ctx->bin_cursor);
         LaunchHot<C>::digits_bin(st, sc, ctx->infmask, count, first, n, ctx->c, ctx->W, ctx->F, ctx->bin_shift, ctx->nbins, ctx->bin_cursor, ctx->staging);
-        k_bin_scatter<<<cdiv((uint64_t)ctx->W * count, BINSC_TPB * BINSC_EPT), BINSC_TPB, 0, st>>>(ctx->staging, ctx->bucket_off + nb, ctx->cursor, ctx->refs);
+        if (ctx->bin_shift <= BS2_MAX_SHIFT && !ctx->scatter_atomic) {
+            const size_t hist_bytes = (size_t)4 << ctx->bin_shift;
+            if (ctx->bs2_smem < hist_bytes) { CK(cudaFuncSetAttribute(k_bin_scatter_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes)); ctx->bs2_smem = hist_bytes; }
+            uint32_t tile = BS2_TILE;
+            if (const char *e = getenv("B200MSM_SCATTER_TILE_K")) tile = (uint32_t)atoi(e) << 10;      // experiments
+            k_bin_scatter_tiled<<<cdiv((uint64_t)ctx->W * count, tile), BS2_TPB, hist_bytes, st>>>(ctx->staging, ctx->bucket_off, nb, ctx->bin_shift, tile, ctx->cursor, ctx->refs);
+        } else {
+            k_bin_scatter<<<cdiv((uint64_t)ctx->W * count, BINSC_TPB * BINSC_EPT), BINSC_TPB, 0, st>>>(ctx->staging, ctx->bucket_off + nb, ctx->cursor, ctx->refs);
+        }
         launches += 2;
     } else {
         LaunchHot<C>::digits(1, st, sc, ctx->infmask, count, first, n, ctx->c, ctx->W, ctx->F, ctx->cursor, ctx->refs);
@@ -628,6 +639,7 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     ctx->curve = curve; ctx->device = device; ctx->req_c = window_bits; ctx->req_tables = tables;
     if (const char *e = getenv("B200MSM_ACC")) ctx->acc_mix = strcmp(e, "fp64") == 0 ? 0 : 8;
     if (const char *e = getenv("B200MSM_HOST_CHUNKS")) ctx->host_chunks = atoi(e);
+    if (const char *e = getenv("B200MSM_SCATTER")) ctx->scatter_atomic = strcmp(e, "atomic") == 0;
     if (const char *g = getenv("B200MSM_GROUP")) if (curve == 0 && strcmp(g, "xyzz") == 0) ctx->kind = 2;
     if (curve == 1) ctx->kind = 1;
     BY_GROUP(ctx->kind, ctx->entry_bytes = LaunchCold<C>::entry_bytes());
