@@ -62,6 +62,7 @@ struct b200msm_ctx {
     int launches = 0;
     int chunks_alloc = 1;     // copies of piece_off / res (one per chunk of a chunked MSM)
     int host_chunks = 0;      // msm_host: split the first batch into this many chunks (0 = by size)
+    int chunk_ratio = 0;      // ... of sizes 1 : q : q^2 ... (B200MSM_CHUNK_RATIO; 0 = 8 for two chunks, 5 for more)
     cudaEvent_t ev_chunk[8] = {};
     int acc_mix = 8;          // accumulate kernel flavour: 8 = integer pipe (default), 0 = FP64 pipe (B200MSM_ACC=fp64)
 
@@ -640,6 +641,7 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     if (const char *e = getenv("B200MSM_ACC")) ctx->acc_mix = strcmp(e, "fp64") == 0 ? 0 : 8;
     if (const char *e = getenv("B200MSM_HOST_CHUNKS")) ctx->host_chunks = atoi(e);
     if (const char *e = getenv("B200MSM_SCATTER")) ctx->scatter_atomic = strcmp(e, "atomic") == 0;
+    if (const char *e = getenv("B200MSM_CHUNK_RATIO")) { int v = atoi(e); if (v >= 2 && v <= 16) ctx->chunk_ratio = v; }
     if (const char *g = getenv("B200MSM_GROUP")) if (curve == 0 && strcmp(g, "xyzz") == 0) ctx->kind = 2;
     if (curve == 1) ctx->kind = 1;
     BY_GROUP(ctx->kind, ctx->entry_bytes = LaunchCold<C>::entry_bytes());
@@ -799,8 +801,9 @@ int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, vo
 // Nothing else can hide the upload of the first batch of a call.  Stands in for the 1/4 + 3/4 split of the reference's
 // fastest entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).  buf: device staging of n x 32 bytes.
 static int default_host_chunks(const b200msm_ctx *ctx, uint64_t n) {
-    // measured: 4 chunks at 2^26 (294.5 -> 272.1 ms) and 2^25, 2 chunks at 2^23 (8 GPUs: 51.4 -> 48.4 ms end to end)
-    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 4 : (n >= (1ull << 22) ? 2 : 1));
+    // measured end to end (profiles/r02_chunks.txt): 2^26: 3 chunks of sizes 1 : 5 : 25 236.1 ms, 4 of 1 : 2 : 4 : 8 (round 1) 240.7,
+    // 2 of 1 : 5 238.2; 2^23 (the 8-GPU shard): 2 chunks 1 : 8 39.7 ms, one chunk 40.8
+    int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 3 : (n >= (1ull << 22) ? 2 : 1));
     return nch > 8 ? 8 : nch;
 }
 static int peer_clear_unused_chunks(b200msm_ctx *ctx, int used);
@@ -812,10 +815,15 @@ static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_
     CK(cudaStreamWaitEvent(ctx->copy_stream, buf_free, 0));
     // chunk sizes double (1 : 2 : 4 : ...): only the first chunk's upload is exposed, and accumulation (3.8 ns per point)
     // is so much slower than the upload (0.6 ns per point) that every later chunk is in place long before it is needed
-    const uint64_t denom = (1ull << nch) - 1;
+    // chunk sizes grow geometrically (1 : q : q^2 ...): only the first chunk's upload is exposed.  q up to ~5 keeps every later
+    // chunk in place before it is needed (accumulation 3.1 ns per point against 0.6 ns of upload)
+    uint64_t q = ctx->chunk_ratio > 0 ? (uint64_t)ctx->chunk_ratio : (nch <= 2 ? 8 : 5), pw[9] = {1};
+    for (int i = 1; i <= nch; i++) pw[i] = pw[i - 1] * q;
+    const uint64_t denom = (pw[nch] - 1) / (q - 1);          // 1 + q + ... + q^(nch-1)
+    auto upto = [&](int ch) { return n * ((pw[ch] - 1) / (q - 1)) / denom; };
     int used = 0;
     for (int ch = 0; ch < nch; ch++) {
-        const uint64_t first = n * ((1ull << ch) - 1) / denom, end = ch + 1 == nch ? n : n * ((1ull << (ch + 1)) - 1) / denom;
+        const uint64_t first = upto(ch), end = ch + 1 == nch ? n : upto(ch + 1);
         const uint64_t cnt = end - first;
         if (cnt == 0) continue;                  // tiny n: fewer, non-empty chunks
         rc = h2d(ctx, buf + first * 32, scalars_host + first * 32, (size_t)cnt * 32, ctx->copy_stream); if (rc) return rc;
