@@ -110,6 +110,57 @@ __global__ void __launch_bounds__(BIN_TPB) k_digits_bin(const uint32_t *__restri
 // The next entry (144 / 112 bytes) is fetched with 16-byte cp.async into the thread's own shared-memory slots
 // ([stage][16-byte chunk][thread]: conflict-free) while the current mixed add (~5000 integer instructions) runs, so the
 // random gather latency is hidden by one stage of prefetch.  Results go to res[piece].
+#if defined(ACC_TMA)
+// Experiment switch (-DACC_TMA=1; north_star asks for TMA staging, DESIGN.md section 6 explains why the default is cp.async):
+// the entry gather as one TMA bulk copy per lane (cp.async.bulk global -> shared, 144 contiguous bytes into the thread's own
+// slot, completion counted on a per-warp mbarrier per stage), two stages.  Same results; measured slower than the nine 16-byte
+// cp.async per lane: UBLKCP takes uniform-register operands, so a warp's 32 different source addresses are issued lane by
+// lane (profiles/r02_acc_tma.txt has the SASS and the timing).
+__device__ __forceinline__ uint32_t hot_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <class C, class ACC>
+__device__ __forceinline__ void accumulate_piece_tma(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
+                                                     uint32_t start, uint32_t len, uint4 *slots /* [2][ACC_TPB][EV] */, uint64_t *bars /* [2][warps] */, xyzz_t *__restrict__ dst) {
+    constexpr int EV = Grp<C>::ENTRY_VEC;
+    constexpr uint32_t BYTES = EV * 16;
+    const uint32_t warp = threadIdx.x >> 5;
+    typename ACC::acc_t acc;
+    ACC::init(acc);
+    // every lane of the warp walks the same number of iterations (the longest piece of the warp): the barrier counts 32 arrivals
+    uint32_t wlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const uint32_t t = __shfl_xor_sync(0xffffffffu, wlen, o); wlen = t > wlen ? t : wlen; }
+    auto issue = [&](uint32_t i) {
+        const uint32_t st = i & 1;
+        uint64_t *bar = bars + st * (ACC_TPB / 32) + warp;
+        if (i < len) {
+            const uint32_t ref = __ldg(refs + start + i);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the slot's last generic reads precede the asynchronous refill
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hot_smem_u32(bar)), "r"(BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hot_smem_u32(slots + ((size_t)st * ACC_TPB + threadIdx.x) * EV)),
+                         "l"(tables + (ref & 0x7fffffffu)), "r"(BYTES), "r"(hot_smem_u32(bar)) : "memory");
+            return ref;
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hot_smem_u32(bar)) : "memory");
+        return 0u;
+    };
+    uint32_t ref = issue(0), ref_next = 0;
+    for (uint32_t i = 0; i < wlen; i++) {
+        if (i + 1 < wlen) ref_next = issue(i + 1);
+        uint64_t *bar = bars + (i & 1) * (ACC_TPB / 32) + warp;
+        uint32_t done;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(hot_smem_u32(bar)), "r"((i >> 1) & 1) : "memory");
+        } while (!done);
+        if (i < len) ACC::madd_staged(acc, slots + ((size_t)(i & 1) * ACC_TPB + threadIdx.x) * EV, 1, (ref >> 31) != 0);
+        __syncwarp();                        // every lane has read its slot before the stage is refilled
+        ref = ref_next;
+    }
+    if (!dst) return;
+    xyzz_t out;
+    ACC::export_to(out, acc);
+    store_xyzz(dst, out);
+}
+#endif
 template <class C, class ACC>
 __device__ __forceinline__ void accumulate_piece(const typename Grp<C>::entry_t *__restrict__ tables, const uint32_t *__restrict__ refs,
                                                  uint32_t start, uint32_t len, uint4 (*stage)[Grp<C>::ENTRY_VEC][ACC_TPB], xyzz_t *__restrict__ dst) {
@@ -150,8 +201,21 @@ __global__ void __launch_bounds__(ACC_TPB, ACC_MINB) k_accumulate(const typename
                                                            const uint32_t *__restrict__ piece_len, const uint32_t *__restrict__ npieces_ptr,
                                                            xyzz_t *__restrict__ res) {
     typedef Grp<C> G;
-    __shared__ uint4 stage[2][G::ENTRY_VEC][ACC_TPB];
     uint32_t j = blockIdx.x * ACC_TPB + threadIdx.x;
+#if defined(ACC_TMA)
+    if constexpr (C::HAS_TE && !FP64) {
+        __shared__ __align__(128) uint4 slots[2 * ACC_TPB * G::ENTRY_VEC];
+        __shared__ __align__(8) uint64_t bars[2 * (ACC_TPB / 32)];
+        if (threadIdx.x < 2 * (ACC_TPB / 32)) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hot_smem_u32(&bars[threadIdx.x])), "r"(32) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+        const bool live = j < *npieces_ptr;                    // whole warps stay: the per-warp barriers count 32 arrivals
+        const uint32_t piece = live ? order[j] : 0;
+        accumulate_piece_tma<C, AccTe29<C>>(tables, refs, live ? piece_start[piece] : 0, live ? piece_len[piece] : 0, slots, bars, live ? res + piece : nullptr);
+        return;
+    }
+#endif
+    __shared__ uint4 stage[2][G::ENTRY_VEC][ACC_TPB];
     if (j >= *npieces_ptr) return;
     const uint32_t piece = order[j];
     const uint32_t start = piece_start[piece], len = piece_len[piece];

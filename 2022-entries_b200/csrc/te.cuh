@@ -26,9 +26,13 @@
 
 namespace b200msm {
 
+#if defined(TE_ENTRY_160)
+struct te_entry_t { uint32_t w[36]; uint32_t pad[4]; };      // experiment: 160-byte, 32-byte-aligned entries = exactly 5 DRAM sectors (profiles/r02_entry160.txt)
+#else
 struct te_entry_t { uint32_t w[36]; };       // (y - x, y + x, 2 d x y), each a canonical value bit-packed 12 x 32.  Montgomery
                                              // form: 2^406 for the integer accumulator (fp29.cuh: unpacking in the hot loop is
                                              // bit slicing), 2^384 (arkworks') when the context runs the FP64-pipe accumulator
+#endif
 struct te_pre_t { fp ymx, ypx, kt; };        // the same in registers
 
 template <class C> struct Te {

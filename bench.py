@@ -36,7 +36,7 @@ METRIC = "BLS12-377 G1 MSM 2^{lg} points/s"
 WORKLOAD = ("BLS12-377 G1 MSM 2^{lg}, one batch, bases resident (harness generator shape: 2^15 distinct points replicated), "
             "uniform 253-bit scalars")
 SEED_BASES, SEED_SCALARS, DISTINCT = 77, 1234, 1 << 15
-TRAFFIC_FILE = "r01_traffic.json"      # ncu --set full capture behind roofline.traffic
+TRAFFIC_FILE = "r02_traffic.json"      # ncu --set full capture behind roofline.traffic
 REF_SAMPLE_LOG_N = 22          # the CPU arm's sample, the same on every host
 
 

@@ -26,8 +26,27 @@ def build(item):
     return name, (f"regs {m.group(2)}, {m.group(1)}" if m else "?") + f"   [{flags}]"
 
 
+def build_full(item):
+    """every translation unit with the flags (layout experiments that touch cold and hot code alike)"""
+    name, flags = item
+    objs = []
+    for tu in ("msm", "inst_hot_377", "inst_hot_381", "inst_hot_377x", "inst_cold_377", "inst_cold_381", "inst_cold_377x"):
+        obj = os.path.join(OUT, f"full_{name}_{tu}.o")
+        r = subprocess.run([NVCC] + BASE + flags.split() + ["-c", "-o", obj, os.path.join(CSRC, tu + ".cu")], capture_output=True, text=True)
+        if r.returncode:
+            return name, "COMPILE FAILED " + tu + "\n" + r.stderr[-1500:]
+        objs.append(obj)
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", os.path.join(OUT, f"lib_{name}.so")] + objs)
+    return name, f"full build   [{flags}]"
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--full" in sys.argv:
+        for a in sys.argv[1:]:
+            if a != "--full":
+                print("%s: %s" % build_full(a.split("=", 1)), flush=True)
+        return
     items = [a.split("=", 1) for a in sys.argv[1:]]
     with ThreadPoolExecutor(4) as ex:
         for name, info in ex.map(build, items):
