@@ -218,7 +218,12 @@ __global__ void __launch_bounds__(BS2_TPB) k_bin_scatter_tiled(const uint2 *__re
         const uint32_t end = bin_end < t1 ? bin_end : t1;
         for (uint32_t b = threadIdx.x; b < per_bin; b += BS2_TPB) bs2_hist[b] = 0;
         __syncthreads();
-        for (uint32_t i = pos + threadIdx.x; i < end; i += BS2_TPB) atomicAdd(&bs2_hist[staging[i].x & mask], 1u);
+        // (both passes: a warp whose lanes all hold the same key -- skewed scalar sets -- does one shared-memory atomic for the warp)
+        for (uint32_t i = pos + threadIdx.x; i < end; i += BS2_TPB) {
+            const uint32_t b = staging[i].x & mask, act = __activemask(), lead = __ffs(act) - 1;
+            if (__all_sync(act, b == __shfl_sync(act, b, lead))) { if ((threadIdx.x & 31) == lead) atomicAdd(&bs2_hist[b], (uint32_t)__popc(act)); }
+            else atomicAdd(&bs2_hist[b], 1u);
+        }
         __syncthreads();
         for (uint32_t b = threadIdx.x; b < per_bin; b += BS2_TPB) {
             const uint32_t c = bs2_hist[b];
@@ -227,7 +232,14 @@ __global__ void __launch_bounds__(BS2_TPB) k_bin_scatter_tiled(const uint2 *__re
         __syncthreads();
         for (uint32_t i = pos + threadIdx.x; i < end; i += BS2_TPB) {
             const uint2 v = __ldcs(staging + i);
-            refs[atomicAdd(&bs2_hist[v.x & mask], 1u)] = v.y;
+            const uint32_t b = v.x & mask, act = __activemask(), lead = __ffs(act) - 1;
+            uint32_t slot;
+            if (__all_sync(act, b == __shfl_sync(act, b, lead))) {
+                uint32_t first = 0;
+                if ((threadIdx.x & 31) == lead) first = atomicAdd(&bs2_hist[b], (uint32_t)__popc(act));
+                slot = __shfl_sync(act, first, lead) + __popc(act & ((1u << (threadIdx.x & 31)) - 1));
+            } else slot = atomicAdd(&bs2_hist[b], 1u);
+            refs[slot] = v.y;
         }
         __syncthreads();
         pos = end;

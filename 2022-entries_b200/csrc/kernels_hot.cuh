@@ -28,7 +28,14 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t *__restrict__ sca
     const uint32_t gi = first + i;
     if (infmask[gi >> 5] & (1u << (gi & 31))) return;     // base at infinity contributes nothing
     if (PASS == 0 && W <= 16) {        // large problems: compile-time trip count
-        for_each_digit<C, 16>(scalars, i, gi, table_stride, c, W, F, [&](int, uint32_t key, uint32_t) { atomicAdd(&counters[key], 1u); });
+        // A warp whose lanes all hit the SAME counter (skewed scalar sets: all-equal, tiny, sparse -- SURVEY A3) adds once for the
+        // warp: 2^24 equal scalars otherwise serialise 1.8e8 atomics on 11 addresses (digits_hist 14.8 ms, profiles/r02_skew.txt)
+        for_each_digit<C, 16>(scalars, i, gi, table_stride, c, W, F, [&](int, uint32_t key, uint32_t) {
+            const uint32_t act = __activemask();
+            const uint32_t k0 = __shfl_sync(act, key, __ffs(act) - 1);
+            if (__all_sync(act, key == k0)) { if ((threadIdx.x & 31) == (uint32_t)(__ffs(act) - 1)) atomicAdd(&counters[key], (uint32_t)__popc(act)); }
+            else atomicAdd(&counters[key], 1u);
+        });
         return;
     }
     for_each_digit<C>(scalars, i, gi, table_stride, c, W, F, [&](uint32_t key, uint32_t ref) {
