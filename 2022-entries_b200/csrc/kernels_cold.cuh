@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) k_block_sum(const xyzz_t *__restrict__ in
 // <= 32 points:   kind 0: 2^shift * sum(arr)        kind 1: 2^shift * sum_k k * arr[k]
 // window value = sum of its terms; result = Horner over windows with c doublings; then either the XYZZ value is
 // stored (partial result of one GPU) or it is exported as an arkworks G1Projective (export_jacobian).
-#define FIN_WARPS 8
+#define FIN_WARPS 12     // one warp per term for the plans in use (8 - 11 terms): the longest term, not a warp's queue, is the critical path (static shared memory: 46 KB)
 template <class C> __device__ void warp_sum(xyzz_t &v, xyzz_t *sh) {
     // tree sum of the 32 lanes' points through shared memory; result in lane 0
     const int lane = threadIdx.x & 31;
@@ -240,14 +240,21 @@ template <class C> __device__ void export_jacobian(const xyzz_t &total, uint32_t
 #pragma unroll
     for (int i = 0; i < 12; i++) { out_jac[i] = ox.w[i]; out_jac[12 + i] = oy.w[i]; out_jac[24 + i] = oz.w[i]; }
 }
+// One block per folded window f: the window's value (its terms, one warp each), times 2^(c f) by lane 0 (c f doublings: the
+// serial part, so the windows do theirs side by side instead of one Horner chain of c (F - 1) doublings plus F term rounds in
+// one block -- 9.4 ms of a 132 ms one-call MSM at 2^24 with F = 15, profiles/r01_one_call_launches_2pow24.txt); the block that
+// finishes last sums the F products and exports.  F = 1 (every resident-bases plan that fits its tables): one block, no hand-over.
 template <class C>
-__global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_t *__restrict__ out_xyzz, uint32_t *__restrict__ out_jac) {
+__global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_t *__restrict__ out_xyzz, uint32_t *__restrict__ out_jac,
+                                                           xyzz_t *__restrict__ scratch, uint32_t *__restrict__ ticket) {
     __shared__ xyzz_t sh[FIN_WARPS][16];
     __shared__ xyzz_t slot[FIN_WARPS];
+    __shared__ uint32_t is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x;
     xyzz_t total;                       // meaningful in thread 0
     Grp<C>::set_inf(total);
-    for (int f = a.F - 1; f >= 0; f--) {
+    {
         xyzz_t part;                    // this warp's share of the window value (lane 0)
         Grp<C>::set_inf(part);
         for (int ti = warp; ti < a.nterms; ti += FIN_WARPS) {
@@ -277,12 +284,31 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) k_finalize(fin_args_t a, xyzz_
             Grp<C>::set_inf(v);
             if (lane < FIN_WARPS) load_xyzz(v, &slot[lane]);
             warp_sum<C>(v, sh[0]);
-            if (lane == 0) {
-                if (f != a.F - 1) for (int s = 0; s < a.c; s++) Grp<C>::dbl_ni(total);
-                Grp<C>::add_ni(total, v);
-            }
+            if (lane == 0) total = v;
+        }
+    }
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < a.c * f; s++) Grp<C>::dbl_ni(total);
+            store_xyzz(scratch + f, total);
+            __threadfence();
+            is_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
         }
         __syncthreads();
+        if (!is_last || warp != 0) return;
+        __threadfence();
+        xyzz_t v;
+        Grp<C>::set_inf(v);
+        for (uint32_t k = lane; k < gridDim.x; k += 32) {
+            xyzz_t w;
+            const uint4 *src = reinterpret_cast<const uint4 *>(scratch + k);
+            uint4 *t = reinterpret_cast<uint4 *>(&w);
+#pragma unroll
+            for (int i = 0; i < XYZZ_VEC; i++) t[i] = __ldcg(src + i);
+            Grp<C>::add_ni(v, w);
+        }
+        warp_sum<C>(v, sh[0]);
+        if (lane == 0) { total = v; *ticket = 0; }
     }
     if (warp != 0 || lane != 0) return;
     if (out_xyzz) store_xyzz(out_xyzz, total);

@@ -40,7 +40,7 @@ template <class C> struct LaunchCold {
     static void block_sum(cudaStream_t st, const xyzz_t *in, uint32_t ngroups, uint32_t group, xyzz_t *out);
     static void peer_merge(cudaStream_t st, const red_src_t *srcs, uint32_t nsrc, uint32_t bucket_base, uint32_t nslice, xyzz_t *merged,
                            const uint32_t *wait_flags, uint32_t wait_n, uint32_t epoch);
-    static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac);
+    static void finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, xyzz_t *scratch, uint32_t *ticket);
     static void combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac);
     static void double_n(cudaStream_t st, const affine_t *src, uint32_t n, int k, xyzz_t *tmp);
     static void batch_normalize(cudaStream_t st, const xyzz_t *tmp, uint32_t n, affine_t *dst, const uint32_t *infmask, uint32_t *bad);

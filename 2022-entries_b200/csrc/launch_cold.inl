@@ -23,8 +23,8 @@ template <class C> void LaunchCold<C>::block_sum(cudaStream_t st, const xyzz_t *
     k_block_sum<C><<<ngroups, group < 128 ? group : 128, 0, st>>>(in, group, out);
 }
 template <class C>
-void LaunchCold<C>::finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac) {
-    k_finalize<C><<<1, 32 * 8, 0, st>>>(a, out_xyzz, out_jac);
+void LaunchCold<C>::finalize(cudaStream_t st, const fin_args_t &a, xyzz_t *out_xyzz, uint32_t *out_jac, xyzz_t *scratch, uint32_t *ticket) {
+    k_finalize<C><<<a.F, 32 * FIN_WARPS, 0, st>>>(a, out_xyzz, out_jac, scratch, ticket);
 }
 template <class C> void LaunchCold<C>::combine(cudaStream_t st, const xyzz_t *parts, int count, uint32_t *out_jac) {
     k_combine<C><<<1, 32, 0, st>>>(parts, count, out_jac);

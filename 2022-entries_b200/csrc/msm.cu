@@ -81,6 +81,8 @@ struct b200msm_ctx {
     size_t bs2_smem = 0;                // dynamic shared memory k_bin_scatter_tiled has been configured for
     bool scatter_atomic = false;        // B200MSM_SCATTER=atomic: the round-1 second level (one global atomic per reference)
     xyzz_t *res = nullptr, *red_buf = nullptr, *part_xyzz = nullptr;
+    xyzz_t *fin_scratch = nullptr;      // k_finalize: one product per folded window
+    uint32_t *fin_ticket = nullptr;
     uint8_t *scal_buf[2] = {nullptr, nullptr};
     uint8_t *raw_buf[2] = {nullptr, nullptr};   // one-call form: arkworks records of one upload step, double-buffered
     affine_t *sw_buf = nullptr;                 //                the same step in the device representation
@@ -141,10 +143,10 @@ struct b200msm_ctx {
     }
     void free_plan() {
         void *ptrs[] = {tables, infmask, bad, counts, bucket_off, cursor, piece_off, piece_start, piece_len, order, len_hist, len_cursor,
-                        scan_tmp, refs, res, red_buf, part_xyzz, scal_buf[0], scal_buf[1], bin_cursor, staging, raw_buf[0], raw_buf[1], sw_buf};
+                        scan_tmp, refs, res, red_buf, part_xyzz, fin_scratch, fin_ticket, scal_buf[0], scal_buf[1], bin_cursor, staging, raw_buf[0], raw_buf[1], sw_buf};
         for (void *p : ptrs) if (p) cudaFree(p);
         tables = nullptr; infmask = nullptr; bad = nullptr; counts = bucket_off = cursor = piece_off = piece_start = piece_len = order = len_hist = len_cursor = nullptr;
-        scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
+        scan_tmp = refs = nullptr; res = red_buf = part_xyzz = nullptr; fin_scratch = nullptr; fin_ticket = nullptr; scal_buf[0] = scal_buf[1] = nullptr; bin_cursor = nullptr; staging = nullptr; nbins = 0;
         raw_buf[0] = raw_buf[1] = nullptr; sw_buf = nullptr; raw_cap = 0;
         if (src_tab) cudaFree(src_tab);
         src_tab = nullptr; src_tab_chunks = -1;
@@ -281,6 +283,9 @@ static int alloc_plan(b200msm_ctx *ctx, uint64_t n) {
     CK(dmalloc(&ctx->refs, (size_t)ctx->max_refs + 1));
     CK(dmalloc(&ctx->res, (size_t)ctx->max_pieces));
     CK(dmalloc(&ctx->part_xyzz, 1));
+    CK(dmalloc(&ctx->fin_scratch, (size_t)ctx->F));
+    CK(dmalloc(&ctx->fin_ticket, 1));
+    CK(cudaMemsetAsync(ctx->fin_ticket, 0, 4, ctx->stream));
     // two-level scatter when the list array is far beyond L2: bins of <= 24 MB of list each, at most BIN_MAX bins
     ctx->nbins = 0;
     // from 256 MB of lists on.  Measured (profiles/r02_scaling.txt): 2^23 points, c = 23, 369 MB of lists (the 8-GPU shard of
@@ -573,7 +578,7 @@ template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *
         launches++;
     }
     cudaEventRecord(ctx->ev[5], st);
-    LaunchCold<C>::finalize(st, peer ? P.fin : ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac);
+    LaunchCold<C>::finalize(st, peer ? P.fin : ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac, ctx->fin_scratch, ctx->fin_ticket);
     launches++;
     cudaEventRecord(ctx->ev[6], st);
     ctx->ev_last[(ctx->ev_sets - 1) % b200msm_ctx::EV_RING] = 6;

@@ -19,7 +19,7 @@ template <class C> static void fp_ops(int op, const fp_abi *a, const fp_abi *b, 
         case 1: F::add(t, x, y); break;
         case 2: F::template sub<2>(t, x, y); break;
         case 3: F::sqr(t, x); break;
-        case 4: F::inv(t, x); break;
+        case 4: Ec<C>::inv_ni(t, x); break;         // the windowed inversion the kernels call (ec.cuh)
         case 6: F::mul_karatsuba(t, x, y); break;
         default: t = x;                       // 5: ABI round trip
         }
