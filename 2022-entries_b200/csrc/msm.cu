@@ -62,7 +62,7 @@ struct b200msm_ctx {
     int launches = 0;
     int chunks_alloc = 1;     // copies of piece_off / res (one per chunk of a chunked MSM)
     int host_chunks = 0;      // msm_host: split the first batch into this many chunks (0 = by size)
-    int chunk_ratio = 0;      // ... of sizes 1 : q : q^2 ... (B200MSM_CHUNK_RATIO; 0 = 8 for two chunks, 5 for more)
+    int chunk_ratio = 0;      // ... of sizes 1 : q : q^2 ... (B200MSM_CHUNK_RATIO / b200msm_set_host_chunks; 0 = 4)
     cudaEvent_t ev_chunk[8] = {};
     int acc_mix = 8;          // accumulate kernel flavour: 8 = integer pipe (default), 0 = FP64 pipe (B200MSM_ACC=fp64)
 
@@ -716,6 +716,14 @@ int b200msm_set_bucket_arithmetic(b200msm_ctx *ctx, int arithmetic) {
     return 0;
 }
 
+int b200msm_set_host_chunks(b200msm_ctx *ctx, int chunks, int ratio) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    if (chunks < 0 || chunks > 8 || (ratio != 0 && (ratio < 2 || ratio > 16))) return ctx->fail(-1, "b200msm_set_host_chunks: chunks 0..8 (0 = by size), ratio 0 (default) or 2..16");
+    ctx->host_chunks = chunks;
+    ctx->chunk_ratio = ratio;
+    return 0;
+}
+
 int b200msm_set_bases(b200msm_ctx *ctx, const void *affine_host, uint64_t n, uint64_t stride) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!affine_host || n == 0 || n >= (1ull << 31) || stride < 96 || (stride & 7)) return ctx->fail(-1, "b200msm_set_bases: bad argument");
@@ -806,7 +814,7 @@ int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, vo
 // Nothing else can hide the upload of the first batch of a call.  Stands in for the 1/4 + 3/4 split of the reference's
 // fastest entry (P1A/combined-top-solutions/combined-msm/MSM.cu:419-435, 477-492).  buf: device staging of n x 32 bytes.
 static int default_host_chunks(const b200msm_ctx *ctx, uint64_t n) {
-    // measured end to end (profiles/r02_chunks.txt): 2^26: 3 chunks of sizes 1 : 5 : 25 236.1 ms, 4 of 1 : 2 : 4 : 8 (round 1) 240.7,
+    // measured end to end (profiles/r02_chunks.txt): 2^26: 3 chunks of sizes 1 : 4 : 16 236.6 ms (1 : 5 : 25 236.1), 4 of 1 : 2 : 4 : 8 (round 1) 240.7,
     // 2 of 1 : 5 238.2; 2^23 (the 8-GPU shard): 2 chunks 1 : 8 39.7 ms, one chunk 40.8
     int nch = ctx->host_chunks > 0 ? ctx->host_chunks : (n >= (1ull << 24) ? 3 : (n >= (1ull << 22) ? 2 : 1));
     return nch > 8 ? 8 : nch;
@@ -822,7 +830,9 @@ static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_
     // is so much slower than the upload (0.6 ns per point) that every later chunk is in place long before it is needed
     // chunk sizes grow geometrically (1 : q : q^2 ...): only the first chunk's upload is exposed.  q up to ~5 keeps every later
     // chunk in place before it is needed (accumulation 3.1 ns per point against 0.6 ns of upload)
-    uint64_t q = ctx->chunk_ratio > 0 ? (uint64_t)ctx->chunk_ratio : (nch <= 2 ? 8 : 5), pw[9] = {1};
+    // default ratio 4: within 0.5 ms of the best measured on one GPU (1 : 5 : 25 at 2^26, 1 : 8 at 2^23) and still safe when the
+    // ranks of an 8-GPU box share the host's links (27 GB/s per GPU: 8 x B200, 2^23 points each: 1 : 4 41.6 ms, 1 : 8 44.1 ms)
+    uint64_t q = ctx->chunk_ratio > 0 ? (uint64_t)ctx->chunk_ratio : 4, pw[9] = {1};
     for (int i = 1; i <= nch; i++) pw[i] = pw[i - 1] * q;
     const uint64_t denom = (pw[nch] - 1) / (q - 1);          // 1 + q + ... + q^(nch-1)
     auto upto = [&](int ch) { return n * ((pw[ch] - 1) / (q - 1)) / denom; };

@@ -12,6 +12,8 @@ P1A/matter-labs/src/lib.rs:86).
 The per-rank engine is injected so that the host logic (slicing, exchange, combine order) runs under gloo on CPU in the
 tests, with a checker standing in for the CUDA engine; the product path constructs it over `Engine` (libb200msm.so).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -90,6 +92,10 @@ class ShardedMsm:
         self.gathered = backend.new_buffer(backend.partial_bytes * self.world)
         self.out = backend.new_buffer(backend.out_bytes)
         self.peers = 0          # chunks the peer mapping was attached with; 0 = every rank reduces all of its own buckets
+        # pageable host scalars are staged by a pool of host threads per process (csrc/copy_pool.h, default: half the cores):
+        # G ranks on one host share its cores
+        if self.world > 1 and "B200MSM_COPY_THREADS" not in os.environ:
+            os.environ["B200MSM_COPY_THREADS"] = str(max(2, (os.cpu_count() or 8) // (2 * self.world)))
 
     def attach_peers(self, chunks=1):
         """Collective: switch to the bucket reduce-scatter -- rank g reduces the buckets [g B / G, (g + 1) B / G) of EVERY rank,

@@ -352,7 +352,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         if world > 1 and sh.peers:
-            sh.attach_peers(chunks=3 if n_local >= (1 << 24) else 2 if n_local >= (1 << 22) else 1)      # the chunked upload keeps one bucket array per chunk (msm.cu upload_and_run)
+            sh.attach_peers(chunks=3 if n_local >= (1 << 24) else 2 if n_local >= (1 << 22) else 1)      # = the library's default split of a host-memory call      # the chunked upload keeps one bucket array per chunk (msm.cu upload_and_run)
         pageable_scal = torch.empty(n_local * 32, dtype=torch.uint8)
         pageable_scal.copy_(host_scal)
         res_holder = {}

@@ -56,6 +56,12 @@ int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream);
  * and the one-call form, which have no such argument). */
 int b200msm_set_bucket_arithmetic(b200msm_ctx *ctx, int arithmetic);
 
+/* How a call that takes scalars from host memory splits its FIRST batch so that the upload overlaps the accumulation: `chunks`
+ * pieces of sizes 1 : ratio : ratio^2 ... (0 = chosen by size: 3 pieces from 2^24 points, 2 from 2^22; ratio 4).  Only the
+ * first piece's upload is exposed; a ratio up to (accumulation time per point) / (upload time per point) keeps every later
+ * piece in place before it is needed -- ~5 on one GPU with a PCIe link of its own, ~2 when 8 GPUs share the host. */
+int b200msm_set_host_chunks(b200msm_ctx *ctx, int chunks, int ratio);
+
 /* multi_scalar_mult_init: upload `n` arkworks G1Affine records (stride bytes apart, 96 <= stride; a base is at infinity
  * when its flag byte at offset 96 is set (stride > 96) or when x = y = 0, the encoding of the flag-less 96-byte
  * blst_p1_affine records, sppark ec/xyzz_t.hpp:44-45) and build the base tables 2^(c*F*j) * P_i.  Replaces
