@@ -181,16 +181,17 @@ def run_reference(args):
     from oracle import oracle as O
     O.build()
     lg = args.log_n
-    # ONE sample size whatever the host: 2^22 points per step (~4 s on 16 cores; arkworks' window rule gives c = 17, 15 windows
-    # = 15 threads there, against c = 19, 14 windows at 2^26).  More than 12 steps + warm-ups in all are capped so that the run
-    # ends within a few minutes; the per-step time does not depend on the count.
+    # ONE sample size whatever the host: 2^22 points per step (~4 s on 16 cores: 25 steps in 100 s; arkworks' window rule gives
+    # c = 17, 15 windows = 15 threads there, against c = 19, 14 windows at 2^26).  Only a host so slow that K + W such steps would
+    # take more than 7 minutes gets the smaller fixed sample 2^20, and the line says so.
     ls = min(REF_SAMPLE_LOG_N, lg)
     cpu_oracle_rate(O, 16)
-    total = args.steps + args.warmup
-    if total > 12:
-        args.warmup = min(args.warmup, 2)
-        args.steps = max(1, min(args.steps, 12 - args.warmup))
-    for _ in range(args.warmup):
+    note = ""
+    _, t_first = cpu_oracle_rate(O, ls)              # first warm-up step, also the guard: K + W steps must end within minutes
+    if t_first * (args.steps + args.warmup) > 420.0 and ls > 20:
+        note = f" (a 2^{ls} step takes {t_first:.1f} s on this host: sample reduced to 2^20 so that {args.steps} + {args.warmup} steps end within minutes)"
+        ls = 20
+    for _ in range(max(args.warmup - 1, 0) if not note else args.warmup):
         cpu_oracle_rate(O, ls)
     pure = 0.0                      # the MSM call alone is timed; input generation is outside
     for _ in range(args.steps):
@@ -201,7 +202,7 @@ def run_reference(args):
     cores = ark_threads(O, 1 << ls)
     c_s, c_f = O.window_bits(1 << ls), O.window_bits(1 << lg)
     sample = (f"2^{ls} points per step, fixed (harness-shaped: 2^10 distinct bases replicated, uniform scalars), arkworks window rule c={c_s} "
-              f"({-(-253 // c_s)} windows = threads); at 2^{lg} the rule gives c={c_f} ({-(-253 // c_f)} windows)")
+              f"({-(-253 // c_s)} windows = threads); at 2^{lg} the rule gives c={c_f} ({-(-253 // c_f)} windows)" + note)
     # one 2^lg MSM at this rate, corrected for the window count: per point the work is one mixed add per window
     extrap_ms = (1 << lg) / value * 1e3 * (-(-253 // c_f)) / (-(-253 // c_s))
     line = {"impl": "reference", "metric": METRIC.format(lg=lg), "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
