@@ -58,6 +58,9 @@ def lib():
     L.b200msm_set_stream.argtypes = [vp, vp]
     L.b200msm_set_bucket_arithmetic.argtypes = [vp, i32]
     L.b200msm_set_host_chunks.argtypes = [vp, i32, i32]
+    L.b200msm_set_pipelined.argtypes = [vp, i32]
+    L.b200msm_result_stream.argtypes = [vp]
+    L.b200msm_result_stream.restype = vp
     L.b200msm_set_bases.argtypes = [vp, vp, u64, u64]
     L.b200msm_set_bases_generated.argtypes = [vp, u64, u64, i32, u64]
     L.b200msm_get_bases.argtypes = [vp, vp, u64, u64]
@@ -108,7 +111,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bucket_arithmetic", "b200msm_set_host_chunks", "b200msm_set_bases",
+    "b200msm_create", "b200msm_destroy", "b200msm_last_error", "b200msm_set_stream", "b200msm_set_bucket_arithmetic", "b200msm_set_host_chunks", "b200msm_set_pipelined", "b200msm_result_stream", "b200msm_set_bases",
     "b200msm_set_bases_generated", "b200msm_get_bases", "b200msm_generate_scalars", "b200msm_msm_device",
     "b200msm_msm_host", "b200msm_msm_partial_device", "b200msm_msm_partial_host", "b200msm_combine_device", "b200msm_sync",
     "b200msm_peer_export", "b200msm_peer_attach", "b200msm_peer_detach", "b200msm_peer_info", "b200msm_msm_peer_partial_device", "b200msm_msm_peer_partial_host",
@@ -317,6 +320,14 @@ class Engine:
     def set_bucket_arithmetic(self, xyzz):
         """xyzz=True: short-Weierstrass XYZZ buckets (complete on every on-curve point); False: the curve's default."""
         self._ck(lib().b200msm_set_bucket_arithmetic(self.h, 1 if xyzz else 0), "set_bucket_arithmetic")
+
+    def set_pipelined(self, on=True):
+        """Consecutive device-resident MSMs overlap: results are then ordered on result_stream() (see include/b200msm.h)."""
+        self._ck(lib().b200msm_set_pipelined(self.h, 1 if on else 0), "set_pipelined")
+
+    def result_stream(self):
+        """Raw cudaStream_t (int) on which results of the device-resident calls are ordered."""
+        return int(lib().b200msm_result_stream(self.h) or 0)
 
     def set_host_chunks(self, chunks=0, ratio=0):
         """Split of the first batch of a host-memory call: `chunks` pieces of sizes 1 : ratio : ratio^2 ... (0 = defaults)."""

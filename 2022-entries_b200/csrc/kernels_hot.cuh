@@ -174,9 +174,13 @@ __device__ __forceinline__ void accumulate_piece(const typename Grp<C>::entry_t 
     constexpr int EV = Grp<C>::ENTRY_VEC;
     typename ACC::acc_t acc;
     ACC::init(acc);
-    uint32_t ref = 0, ref_next = 0;
+    // The list of references is read TWO iterations ahead: the reference of entry i + 1 is already in a register when its
+    // gather is issued (loading it there stalled the warp for an L2 / DRAM round trip per mixed add: long_scoreboard 0.28 per
+    // issue in profiles/r02_ncu_accumulate_fp29.txt).
+    uint32_t ref = 0, ref_next = 0, ref_next2 = 0;
     if (len) {
         ref = __ldg(refs + start);
+        if (len > 1) ref_next = __ldg(refs + start + 1);
         const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref & 0x7fffffffu));
 #pragma unroll
         for (int k = 0; k < EV; k++) cp_async16(&stage[0][k][threadIdx.x], src + k);
@@ -184,15 +188,16 @@ __device__ __forceinline__ void accumulate_piece(const typename Grp<C>::entry_t 
     cp_async_commit();
     for (uint32_t i = 0; i < len; i++) {
         if (i + 1 < len) {
-            ref_next = __ldg(refs + start + i + 1);
             const uint4 *src = reinterpret_cast<const uint4 *>(tables + (ref_next & 0x7fffffffu));
 #pragma unroll
             for (int k = 0; k < EV; k++) cp_async16(&stage[(i + 1) & 1][k][threadIdx.x], src + k);
         }
+        if (i + 2 < len) ref_next2 = __ldg(refs + start + i + 2);
         cp_async_commit();
         cp_async_wait<1>();
         ACC::madd_staged(acc, &stage[i & 1][0][threadIdx.x], ACC_TPB, (ref >> 31) != 0);
         ref = ref_next;
+        ref_next = ref_next2;
     }
     xyzz_t out;
     ACC::export_to(out, acc);

@@ -48,6 +48,16 @@ struct b200msm_ctx {
     int kind = 0;             // BY_GROUP selector: curve, except 2 = BLS12-377 with XYZZ buckets (b200msm_set_bucket_arithmetic)
     int req_c = 0, req_tables = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr, conv_stream = nullptr;   // conv: entry conversion of the one-call form (high priority)
+    // The TAIL of an MSM -- the upper levels of the bucket reduction, finalize, and (multi-GPU) the combine step: a few dozen
+    // dependent curve additions in kernels of 1 .. 64 blocks, ~3 ms that no amount of hardware shortens -- runs on a stream of
+    // its own (high priority), so that the NEXT MSM's digit and scatter kernels fill the GPU meanwhile.  The reference overlaps
+    // the same part of its pipeline, there on the host (yrrid MSM.cu:484-494: hostReduce of batch k under the kernels of batch
+    // k + 1).  msm_host / the one-call form always work this way; the device-resident calls do when the caller has opted in
+    // (b200msm_set_pipelined) and consumes results on b200msm_result_stream or after b200msm_sync.
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t ev_l0 = nullptr, ev_tail = nullptr;
+    bool tail_pending = false;          // ev_tail has been recorded: the next level 0 must not overwrite the level buffers before it
+    bool pipeline = false;              // b200msm_set_pipelined
     cudaEvent_t ev_conv = nullptr;
     bool own_stream = true;
     std::string err;
@@ -192,6 +202,14 @@ static bool choose_plan(b200msm_ctx *ctx, uint64_t n, size_t free_bytes) {
     ctx->T = (ctx->W + ctx->F - 1) / ctx->F;
     ctx->nbuckets = (uint32_t)ctx->F << (ctx->c - 1);
     return true;
+}
+
+// the context's stream AND the tail stream its MSMs hand their last kernels to
+static cudaError_t sync_streams(b200msm_ctx *ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && ctx->tail_stream) e = cudaStreamSynchronize(ctx->tail_stream);
+    if (e == cudaSuccess) ctx->tail_pending = false;
+    return e;
 }
 
 template <class T> static cudaError_t dmalloc(T **p, size_t count) { return cudaMalloc((void **)p, count * sizeof(T)); }
@@ -400,7 +418,7 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
     }
     CK(cudaMemsetAsync(ctx->infmask, 0, ((size_t)cdiv(n, 32) + 1) * 4, ctx->stream));
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     return 0;
 }
 
@@ -411,7 +429,7 @@ template <class C> static int gen_bases_t(b200msm_ctx *ctx, uint64_t seed, int m
 static int check_bad_entries(b200msm_ctx *ctx) {
     uint32_t bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     if (bad == 0) return 0;
     CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
     ctx->n = 0;                          // the tables are unusable: a later MSM call fails with "bases not set"
@@ -433,7 +451,7 @@ template <class C> static int set_bases_t(b200msm_ctx *ctx, const void *affine_h
         LaunchCold<C>::convert_points(ctx->stream, raw, (uint32_t)cnt, (uint32_t)stride, sc.sw[0], ctx->infmask + first / 32);
         emit_tables<C>(ctx, sc, (uint32_t)first, (uint32_t)cnt, ctx->infmask + first / 32);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(sync_streams(ctx));
     }
     return check_bad_entries(ctx);
 }
@@ -553,12 +571,22 @@ static int local_sources(b200msm_ctx *ctx, int nchunks) {
 }
 // peer = false: every bucket of this GPU (nchunks sources).  peer = true: this rank's slice of the buckets of every GPU
 // (world x chunks sources over NVLink, waiting for the peers' `ready` counters inside the level-0 kernel).
-template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz, bool peer = false) {
+// join: the context's stream waits for the tail before the call returns (the result is ordered on that stream, as the
+// device-resident calls promise); without it the caller orders its consumer after ev_tail itself.
+template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz, bool peer, bool join) {
     cudaStream_t st = ctx->stream;
     int launches = 0;
     if (!peer) { int rc = local_sources(ctx, nchunks); if (rc) return rc; }
     auto &P = ctx->peer;
+    if (ctx->tail_pending) { CK(cudaStreamWaitEvent(st, ctx->ev_tail, 0)); ctx->tail_pending = false; }      // level 0 overwrites what the previous tail reads
+    bool first = true;
     for (const red_step_t &s : peer ? P.steps : ctx->red_steps) {
+        if (!first && st == ctx->stream) {          // level 0 is done on the context's stream: everything after it is the tail
+            CK(cudaEventRecord(ctx->ev_l0, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_l0, 0));
+            st = ctx->tail_stream;
+        }
+        first = false;
         if (s.kind == 2) LaunchCold<C>::block_sum(st, s.in, s.n_out, s.m, s.outS);
         else if (s.kind == 1) LaunchCold<C>::reduce_slices(st, s.in, nullptr, 0, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
         else if (!peer) LaunchCold<C>::reduce_slices(st, nullptr, ctx->src_tab, (uint32_t)nchunks, 0, s.n_out, s.block, s.m, s.outS, s.outT, nullptr, 0, 0);
@@ -577,14 +605,27 @@ template <class C> static int run_reduce_t(b200msm_ctx *ctx, int nchunks, void *
         }
         launches++;
     }
+    if (st == ctx->stream) {                        // a one-level plan: the hand-over still happens before finalize
+        CK(cudaEventRecord(ctx->ev_l0, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_l0, 0));
+        st = ctx->tail_stream;
+    }
     cudaEventRecord(ctx->ev[5], st);
     LaunchCold<C>::finalize(st, peer ? P.fin : ctx->fin, (xyzz_t *)out_xyzz, (uint32_t *)out_jac, ctx->fin_scratch, ctx->fin_ticket);
     launches++;
     cudaEventRecord(ctx->ev[6], st);
+    CK(cudaEventRecord(ctx->ev_tail, st));
+    ctx->tail_pending = true;
+    if (join) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0)); ctx->tail_pending = false; }
     ctx->ev_last[(ctx->ev_sets - 1) % b200msm_ctx::EV_RING] = 6;
     ctx->ev_steps++;
     ctx->launches += launches;
     CK(cudaGetLastError());
+    return 0;
+}
+// the context's stream waits for the last tail (before something on it consumes a result)
+static int join_tail(b200msm_ctx *ctx) {
+    if (ctx->tail_pending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_tail, 0)); ctx->tail_pending = false; }
     return 0;
 }
 static int run_chunk(b200msm_ctx *ctx, const void *scalars_dev, uint32_t first, uint32_t count, int chunk) {
@@ -592,22 +633,22 @@ static int run_chunk(b200msm_ctx *ctx, const void *scalars_dev, uint32_t first, 
     BY_GROUP(ctx->kind, rc = run_chunk_t<C>(ctx, scalars_dev, first, count, chunk));
     return rc;
 }
-static int run_reduce(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz, bool peer = false) {
+static int run_reduce(b200msm_ctx *ctx, int nchunks, void *out_jac, void *out_xyzz, bool peer = false, bool join = true) {
     int rc = 0;
-    BY_GROUP(ctx->kind, rc = run_reduce_t<C>(ctx, nchunks, out_jac, out_xyzz, peer));
+    BY_GROUP(ctx->kind, rc = run_reduce_t<C>(ctx, nchunks, out_jac, out_xyzz, peer, join));
     return rc;
 }
 // one MSM on the context's stream.  scalars: device, n x 32 bytes.  Exactly one of out_jac / out_xyzz is set.
-static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz) {
+static int run_msm(b200msm_ctx *ctx, const void *scalars_dev, void *out_jac, void *out_xyzz, bool join) {
     int rc = run_chunk(ctx, scalars_dev, 0, (uint32_t)ctx->n, 0);
     if (rc) return rc;
-    return run_reduce(ctx, 1, out_jac, out_xyzz);
+    return run_reduce(ctx, 1, out_jac, out_xyzz, false, join);
 }
 // piece_off / res hold one copy per chunk
 static int ensure_chunks(b200msm_ctx *ctx, int k) {
     if (k <= ctx->chunks_alloc) return 0;
     if (ctx->peer.world) return ctx->fail(-1, "the bucket arrays are mapped by peer GPUs and cannot grow: attach with the chunk count the calls will use");
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     cudaFree(ctx->piece_off); cudaFree(ctx->res);
     ctx->piece_off = nullptr; ctx->res = nullptr;
     CK(dmalloc(&ctx->piece_off, (size_t)k * ((size_t)ctx->nbuckets + 1)));
@@ -655,6 +696,9 @@ int b200msm_create(b200msm_ctx **out, int curve, int device, int window_bits, in
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); e = cudaStreamCreateWithPriority(&ctx->conv_stream, cudaStreamNonBlocking, hi); }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_conv, cudaEventDisableTiming);
+    if (e == cudaSuccess) { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi); e = cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, hi); }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_l0, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_tail, cudaEventDisableTiming);
     for (int r = 0; r < b200msm_ctx::EV_RING; r++) for (int i = 0; i < 7 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->evr[r][i]);
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming); if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming); }
@@ -684,6 +728,9 @@ int b200msm_destroy(b200msm_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->conv_stream) cudaStreamDestroy(ctx->conv_stream);
     if (ctx->ev_conv) cudaEventDestroy(ctx->ev_conv);
+    if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
+    if (ctx->ev_l0) cudaEventDestroy(ctx->ev_l0);
+    if (ctx->ev_tail) cudaEventDestroy(ctx->ev_tail);
     delete ctx;
     return 0;
 }
@@ -692,7 +739,7 @@ const char *b200msm_last_error(const b200msm_ctx *ctx) { return ctx ? ctx->err.c
 
 int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream) {
     int rc = check_ctx(ctx); if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     if (cuda_stream) {
         if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
         ctx->stream = (cudaStream_t)cuda_stream;
@@ -709,12 +756,20 @@ int b200msm_set_bucket_arithmetic(b200msm_ctx *ctx, int arithmetic) {
     if (arithmetic != 0 && arithmetic != 1) return ctx->fail(-1, "b200msm_set_bucket_arithmetic: 0 = the curve's default, 1 = XYZZ");
     const int kind = ctx->curve == 1 ? 1 : (arithmetic == 1 ? 2 : 0);
     if (kind == ctx->kind) return 0;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     ctx->free_plan();                     // entry size and tables change: bases must be set again
     ctx->kind = kind;
     BY_GROUP(ctx->kind, ctx->entry_bytes = LaunchCold<C>::entry_bytes());
     return 0;
 }
+
+int b200msm_set_pipelined(b200msm_ctx *ctx, int on) {
+    int rc = check_ctx(ctx); if (rc) return rc;
+    CK(sync_streams(ctx));
+    ctx->pipeline = on != 0;
+    return 0;
+}
+void *b200msm_result_stream(b200msm_ctx *ctx) { return ctx ? (void *)(ctx->pipeline ? ctx->tail_stream : ctx->stream) : nullptr; }
 
 int b200msm_set_host_chunks(b200msm_ctx *ctx, int chunks, int ratio) {
     int rc = check_ctx(ctx); if (rc) return rc;
@@ -750,7 +805,7 @@ int b200msm_check_bases_in_g1(b200msm_ctx *ctx, uint64_t *outside) {
     BY_GROUP(ctx->kind, LaunchCold<C>::check_order_r(ctx->stream, ctx->tables, ctx->infmask, (uint32_t)ctx->n, ctx->acc_mix == 0, ctx->bad));
     uint32_t cnt = 0;
     CK(cudaMemcpyAsync(&cnt, ctx->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     CK(cudaMemsetAsync(ctx->bad, 0, 4, ctx->stream));
     *outside = cnt;
     return 0;
@@ -770,11 +825,11 @@ int b200msm_set_bases_generated(b200msm_ctx *ctx, uint64_t n, uint64_t seed, int
 int b200msm_get_bases(b200msm_ctx *ctx, void *affine96_host, uint64_t first, uint64_t n) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!affine96_host || first + n > ctx->n) return ctx->fail(-1, "b200msm_get_bases: bad argument");
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     uint32_t *tmp = nullptr;
     CK(cudaMalloc((void **)&tmp, (size_t)n * 96));
     BY_GROUP(ctx->kind, LaunchCold<C>::export_points(ctx->stream, ctx->tables + first * ctx->entry_bytes, (uint32_t)n, tmp, ctx->acc_mix == 0));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     CK(cudaMemcpy(affine96_host, tmp, (size_t)n * 96, cudaMemcpyDeviceToHost));
     cudaFree(tmp);
     return 0;
@@ -792,19 +847,20 @@ int b200msm_generate_scalars(b200msm_ctx *ctx, void *scalars_dev, uint64_t n, ui
 int b200msm_msm_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_jacobian_dev) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!scalars_dev || !out_jacobian_dev || ctx->n == 0 || n != ctx->n) return ctx->fail(-1, "b200msm_msm_device: bad argument (bases not set or length mismatch)");
-    return run_msm(ctx, scalars_dev, out_jacobian_dev, nullptr);
+    return run_msm(ctx, scalars_dev, out_jacobian_dev, nullptr, !ctx->pipeline);
 }
 
 int b200msm_msm_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!scalars_dev || !out_xyzz_dev || ctx->n == 0 || n != ctx->n) return ctx->fail(-1, "b200msm_msm_partial_device: bad argument");
-    return run_msm(ctx, scalars_dev, nullptr, out_xyzz_dev);
+    return run_msm(ctx, scalars_dev, nullptr, out_xyzz_dev, !ctx->pipeline);
 }
 
 int b200msm_combine_device(b200msm_ctx *ctx, const void *xyzz_dev, int count, void *out_jacobian_dev) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!xyzz_dev || count < 1 || !out_jacobian_dev) return ctx->fail(-1, "b200msm_combine_device: bad argument");
-    BY_GROUP(ctx->kind, LaunchCold<C>::combine(ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev));
+    // pipelined contexts: the partials were produced (and gathered) on the tail stream; the combine step continues there
+    BY_GROUP(ctx->kind, LaunchCold<C>::combine(ctx->pipeline ? ctx->tail_stream : ctx->stream, (const xyzz_t *)xyzz_dev, count, (uint32_t *)out_jacobian_dev));
     CK(cudaGetLastError());
     return 0;
 }
@@ -820,7 +876,7 @@ static int default_host_chunks(const b200msm_ctx *ctx, uint64_t n) {
     return nch > 8 ? 8 : nch;
 }
 static int peer_clear_unused_chunks(b200msm_ctx *ctx, int used);
-static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_t n, uint8_t *buf, cudaEvent_t buf_free, void *out_jac, void *out_xyzz, bool peer = false) {
+static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_t n, uint8_t *buf, cudaEvent_t buf_free, void *out_jac, void *out_xyzz, bool peer, bool join) {
     int rc = 0;
     int nch = peer ? ctx->peer.chunks : default_host_chunks(ctx, n);
     if ((uint64_t)nch > n) nch = 1;
@@ -851,9 +907,9 @@ static int upload_and_run(b200msm_ctx *ctx, const uint8_t *scalars_host, uint64_
     if (peer) {
         rc = peer_clear_unused_chunks(ctx, used); if (rc) return rc;
         k_peer_signal<<<1, PEER_MAX, 0, ctx->stream>>>(ctx->peer.flag_ptrs, (uint32_t)ctx->peer.world, (uint32_t)ctx->peer.rank, ctx->peer.epoch);
-        return run_reduce(ctx, ctx->peer.chunks, nullptr, out_xyzz, true);
+        return run_reduce(ctx, ctx->peer.chunks, nullptr, out_xyzz, true, join);
     }
-    return run_reduce(ctx, used, out_jac, out_xyzz);
+    return run_reduce(ctx, used, out_jac, out_xyzz, false, join);
 }
 
 int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, void *out_xyzz_dev) {
@@ -861,7 +917,7 @@ int b200msm_msm_partial_host(b200msm_ctx *ctx, const void *scalars_host, uint64_
     if (!scalars_host || !out_xyzz_dev || ctx->n == 0 || n != ctx->n) return ctx->fail(-1, "b200msm_msm_partial_host: bad argument");
     if (!ctx->scal_buf[0]) CK(cudaMalloc((void **)&ctx->scal_buf[0], (size_t)n * 32));
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
-    return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev);
+    return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev, false, !ctx->pipeline);
 }
 
 // ---- multi-GPU bucket reduce-scatter -------------------------------------------------------------------------------------
@@ -947,7 +1003,7 @@ int b200msm_peer_attach(b200msm_ctx *ctx, int rank, int world, const void *handl
 
 int b200msm_peer_detach(b200msm_ctx *ctx) {
     int rc = check_ctx(ctx); if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     ctx->peer_release();
     return 0;
 }
@@ -956,7 +1012,7 @@ int b200msm_peer_info(b200msm_ctx *ctx, uint64_t info[6]) {
     if (!ctx || !info) return -1;
     info[0] = (uint64_t)ctx->peer.world; info[1] = (uint64_t)ctx->peer.rank; info[2] = (uint64_t)ctx->peer.chunks; info[3] = ctx->peer.nvlink_bytes;
     info[4] = info[5] = 0;
-    if (ctx->peer.world && ctx->peer.epoch && cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+    if (ctx->peer.world && ctx->peer.epoch && sync_streams(ctx) == cudaSuccess) {
         float w = 0.f, m = 0.f;
         if (cudaEventElapsedTime(&w, ctx->peer.ev[0], ctx->peer.ev[1]) == cudaSuccess && cudaEventElapsedTime(&m, ctx->peer.ev[1], ctx->peer.ev[2]) == cudaSuccess) {
             info[4] = (uint64_t)(w * 1000.f); info[5] = (uint64_t)(m * 1000.f);
@@ -987,7 +1043,7 @@ int b200msm_peer_accumulate_device(b200msm_ctx *ctx, const void *scalars_dev, ui
 int b200msm_peer_reduce(b200msm_ctx *ctx, void *out_xyzz_dev) {
     int rc = check_ctx(ctx); if (rc) return rc;
     if (!out_xyzz_dev || !ctx->peer.world || ctx->peer.epoch == 0) return ctx->fail(-1, "b200msm_peer_reduce: bad argument");
-    return run_reduce(ctx, ctx->peer.chunks, nullptr, out_xyzz_dev, true);
+    return run_reduce(ctx, ctx->peer.chunks, nullptr, out_xyzz_dev, true, !ctx->pipeline);
 }
 int b200msm_msm_peer_partial_device(b200msm_ctx *ctx, const void *scalars_dev, uint64_t n, void *out_xyzz_dev) {
     int rc = b200msm_peer_accumulate_device(ctx, scalars_dev, n); if (rc) return rc;
@@ -999,7 +1055,7 @@ int b200msm_msm_peer_partial_host(b200msm_ctx *ctx, const void *scalars_host, ui
     if (!ctx->scal_buf[0]) CK(cudaMalloc((void **)&ctx->scal_buf[0], (size_t)n * 32));
     CK(cudaEventRecord(ctx->ev_free[0], ctx->stream));
     ctx->peer.epoch++;
-    return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev, true);
+    return upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[0], ctx->ev_free[0], nullptr, out_xyzz_dev, true, !ctx->pipeline);
 }
 
 int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uint64_t batches, void *out_jacobian_host) {
@@ -1019,7 +1075,7 @@ int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uin
     for (uint64_t b = 0; b < batches; b++) {
         int k = (int)(b & 1);
         if (b == 0) {
-            rc = upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[k], ctx->ev_free[k], ctx->out_dev, nullptr);
+            rc = upload_and_run(ctx, (const uint8_t *)scalars_host, n, ctx->scal_buf[k], ctx->ev_free[k], ctx->out_dev, nullptr, false, false);
             if (rc) return rc;
             CK(cudaEventRecord(ctx->ev_free[k], ctx->stream));
             continue;
@@ -1028,18 +1084,19 @@ int b200msm_msm_host(b200msm_ctx *ctx, const void *scalars_host, uint64_t n, uin
         rc = h2d(ctx, ctx->scal_buf[k], (const uint8_t *)scalars_host + b * bytes, bytes, ctx->copy_stream); if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));
-        rc = run_msm(ctx, ctx->scal_buf[k], ctx->out_dev + b * 144, nullptr);
+        rc = run_msm(ctx, ctx->scal_buf[k], ctx->out_dev + b * 144, nullptr, false);      // its tail runs beside the next batch's planning
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_free[k], ctx->stream));
     }
+    rc = join_tail(ctx); if (rc) return rc;
     CK(cudaMemcpyAsync(out_jacobian_host, ctx->out_dev, (size_t)batches * 144, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     return 0;
 }
 
 int b200msm_sync(b200msm_ctx *ctx) {
     int rc = check_ctx(ctx); if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     return 0;
 }
 
@@ -1069,7 +1126,7 @@ int b200msm_get_info(const b200msm_ctx *ctx, uint64_t info[8]) {
 // Sums the stage times of the newest `want` complete MSMs still in the ring (every chunk's set counted): walks the sets from
 // the newest back; a set with ev_last == 6 closes an MSM, the sets before it down to the previous closing set are its chunks.
 static int stage_sums(b200msm_ctx *ctx, uint64_t want, float sum[6], uint64_t *covered) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     for (int i = 0; i < 6; i++) sum[i] = 0.f;
     *covered = 0;
     const uint64_t have = ctx->ev_sets < (uint64_t)b200msm_ctx::EV_RING ? ctx->ev_sets : (uint64_t)b200msm_ctx::EV_RING;
@@ -1098,7 +1155,7 @@ int b200msm_get_stage_ms(b200msm_ctx *ctx, float stage_ms[6]) {
 
 int b200msm_reset_stage_stats(b200msm_ctx *ctx) {
     int rc = check_ctx(ctx); if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     ctx->ev_steps = 0;
     ctx->ev_sets = 0;
     return 0;
@@ -1145,7 +1202,7 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
     ctx->h2d_ms = ctx->h2d_wait_ms = 0;
     const uint64_t cap = n < step ? n : step;
     if (ctx->raw_cap < cap * stride) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(sync_streams(ctx));
         for (int i = 0; i < 2; i++) { cudaFree(ctx->raw_buf[i]); ctx->raw_buf[i] = nullptr; }
         ctx->raw_cap = 0;
         for (int i = 0; i < 2; i++) CK(cudaMalloc((void **)&ctx->raw_buf[i], (size_t)(cap * stride)));
@@ -1197,7 +1254,7 @@ template <class C> static int one_call_t(b200msm_ctx *ctx, const uint8_t *bases,
     uint32_t bad = 0;
     CK(cudaMemcpyAsync(&bad, ctx->bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     const double issue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_streams(ctx));
     if (getenv("B200MSM_TRACE")) {
         float st[6] = {};
         uint64_t cov = 0;

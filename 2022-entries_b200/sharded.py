@@ -38,6 +38,13 @@ class CudaShardBackend:
         self.partial_bytes, self.out_bytes = PARTIAL_BYTES, PROJECTIVE_BYTES
         self.n = engine.n
         self.dev_scalars = None
+        self.result_stream = self.stream     # where results of the engine's device-resident calls are ordered
+
+    def set_pipelined(self, on=True):
+        """Consecutive MSMs overlap (the tail of one under the planning kernels of the next, Engine.set_pipelined): the partial,
+        the all-gather and the combine step then live on the engine's tail stream."""
+        self.e.set_pipelined(on)
+        self.result_stream = torch.cuda.ExternalStream(self.e.result_stream(), device=self.device) if on else self.stream
 
     def new_buffer(self, nbytes):
         return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
@@ -142,7 +149,7 @@ class ShardedMsm:
             b.partial_from_host(scalars_dev, self.partial)
         else:
             b.partial(b.upload(scalars_dev) if host else scalars_dev, self.partial)
-        stream = getattr(b, "stream", None)
+        stream = getattr(b, "result_stream", getattr(b, "stream", None))
         if stream is not None:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
@@ -154,7 +161,7 @@ class ShardedMsm:
     def msm(self, scalars_host):
         """End-to-end call: this rank's scalar slice in (pinned) host memory -> 144-byte result on the host."""
         out = self.msm_device(scalars_host, host=True)
-        stream = getattr(self.b, "stream", None)
+        stream = getattr(self.b, "result_stream", getattr(self.b, "stream", None))
         if stream is not None:
             with torch.cuda.stream(stream):
                 host = out.to("cpu", non_blocking=False)

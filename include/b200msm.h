@@ -56,6 +56,16 @@ int b200msm_set_stream(b200msm_ctx *ctx, void *cuda_stream);
  * and the one-call form, which have no such argument). */
 int b200msm_set_bucket_arithmetic(b200msm_ctx *ctx, int arithmetic);
 
+/* Pipelining of consecutive MSMs on one context.  The last ~3 ms of an MSM (upper levels of the bucket reduction, finalize,
+ * the multi-GPU combine) are chains of dependent curve additions in tiny kernels; they run on an internal high-priority stream
+ * so that the next MSM's digit / scatter kernels can fill the GPU meanwhile (the reference overlaps the same part on the host:
+ * yrrid MSM.cu:484-494).  b200msm_msm_host and the one-call form always do this internally.  For the device-resident calls
+ * (b200msm_msm_device, *_partial_*, b200msm_combine_device) it is opt-in, because it changes WHERE the result is ordered:
+ * with pipelining on, the result buffer is written on b200msm_result_stream(ctx) -- consume it there (or after b200msm_sync);
+ * off (default), it is ordered on the context's own stream as documented below. */
+int b200msm_set_pipelined(b200msm_ctx *ctx, int on);
+void *b200msm_result_stream(b200msm_ctx *ctx);      /* cudaStream_t: the context's stream, or the tail stream when pipelined */
+
 /* How a call that takes scalars from host memory splits its FIRST batch so that the upload overlaps the accumulation: `chunks`
  * pieces of sizes 1 : ratio : ratio^2 ... (0 = chosen by size: 3 pieces from 2^24 points, 2 from 2^22; ratio 4).  Only the
  * first piece's upload is exposed; a ratio up to (accumulation time per point) / (upload time per point) keeps every later

@@ -863,3 +863,39 @@ def test_subgroup_check_of_resident_bases(M, oracle):
         e.close()
     finally:
         del os.environ["B200MSM_CHECK_G1"]
+
+
+def test_pipelined_consecutive_msms(M, oracle):
+    """b200msm_set_pipelined: the tail of one MSM (upper reduction levels, finalize) runs on the context's tail stream beside the
+    next MSM's kernels.  Five MSMs with different scalars issued back to back without a synchronisation in between, each into
+    its own output; then the same through partial + combine; every result bit-exact.  The default (off) orders results on the
+    context's stream, which the rest of the suite relies on."""
+    import torch
+    O = oracle
+    n = 1 << 14
+    pts = np.tile(O.gen_points(256, seed=81), (n // 256, 1))
+    e = M.Engine(0, window_bits=13)
+    e.set_bases(pts)
+    e.set_pipelined(True)
+    assert e.result_stream() != 0
+    scs = [O.gen_scalars(n, seed=600 + k) for k in range(5)]
+    dev = [torch.from_numpy(s.reshape(-1).copy()).cuda() for s in scs]
+    outs = torch.zeros(5, 144, dtype=torch.uint8, device="cuda")
+    for k in range(5):
+        e.msm_device(dev[k].data_ptr(), n, outs[k].data_ptr())
+    e.sync()
+    for k in range(5):
+        assert np.array_equal(O.jac_to_affine(outs[k].cpu().numpy()), O.jac_to_affine(O.ark_msm(pts, scs[k]))), k
+    parts = torch.zeros(5, 224, dtype=torch.uint8, device="cuda")
+    for k in range(5):
+        e.msm_partial_device(dev[k].data_ptr(), n, parts[k].data_ptr())
+        e.combine_device(parts[k].data_ptr(), 1, outs[k].data_ptr())          # on the result stream, behind the partial
+    e.sync()
+    for k in range(5):
+        assert np.array_equal(O.jac_to_affine(outs[k].cpu().numpy()), O.jac_to_affine(O.ark_msm(pts, scs[k]))), k
+    e.set_pipelined(False)
+    e.msm_device(dev[0].data_ptr(), n, outs[0].data_ptr())
+    torch.cuda.current_stream().synchronize()
+    e.sync()
+    assert np.array_equal(O.jac_to_affine(outs[0].cpu().numpy()), O.jac_to_affine(O.ark_msm(pts, scs[0])))
+    e.close()
