@@ -102,7 +102,7 @@ class ShardedMsm:
         # pageable host scalars are staged by a pool of host threads per process (csrc/copy_pool.h, default: half the cores):
         # G ranks on one host share its cores
         if self.world > 1 and "B200MSM_COPY_THREADS" not in os.environ:
-            os.environ["B200MSM_COPY_THREADS"] = str(max(2, (os.cpu_count() or 8) // (2 * self.world)))
+            os.environ["B200MSM_COPY_THREADS"] = str(max(4, (os.cpu_count() or 8) // self.world))
 
     def attach_peers(self, chunks=1):
         """Collective: switch to the bucket reduce-scatter -- rank g reduces the buckets [g B / G, (g + 1) B / G) of EVERY rank,
