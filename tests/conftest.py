@@ -56,3 +56,20 @@ def bls381_small_multiples(oracle):
         canon = np.frombuffer(int(x, 16).to_bytes(48, "little") + int(y, 16).to_bytes(48, "little"), np.uint8)
         aff[i, :96] = oracle.fp_convert(canon, True, curve=1).reshape(-1)
     return aff, d["multiples_of_first_point"]
+
+
+@pytest.fixture(scope="session")
+def bls381_hash_to_curve(oracle):
+    """The five RFC 9380 hash-to-curve vectors of arkworks' BLS12-381 G1 tests (tests/golden/bls12_381_hash_to_curve.json):
+    per vector the bases [Q0, Q1] as G1Affine records (uint8[2, 104], Montgomery), the expected P likewise (uint8[104]), and
+    the scalar h_eff with P = h_eff * Q0 + h_eff * Q1."""
+    import json
+    d = json.load(open(os.path.join(GOLDEN, "bls12_381_hash_to_curve.json")))
+
+    def rec(xy):
+        canon = np.frombuffer(int(xy[0], 16).to_bytes(48, "little") + int(xy[1], 16).to_bytes(48, "little"), np.uint8)
+        out = np.zeros(104, np.uint8)
+        out[:96] = oracle.fp_convert(canon, True, curve=1).reshape(-1)
+        return out
+    return [(np.stack([rec(v["Q0"]), rec(v["Q1"])]), rec(v["P"])) for v in d["vectors"]], int(d["h_eff"], 16)
+

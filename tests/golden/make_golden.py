@@ -17,6 +17,14 @@ prize-7 mobile harness into tests/golden/ and records their sha256:
       generator.  They are k*G for k = 1, 2, 3, 5, 4, 6, 7, 8, 9, 9 (established below with affine chord-and-tangent
       arithmetic on Python integers, independent of oracle/); written to bls12_381_small_multiples.json.
 
+  /root/reference/open-division/prize4-msm-wasm/snarkify/zprize-prize4-15ac8c55-arkworks-algebra/ec/src/hashing/tests/testdata/
+      BLS12381G1_XMD-SHA-256_SSWU_RO_.json (the same file, byte for byte, sits in prize1b-msm-fpga/nickray/driver/algebra and
+      prize7-msm-mobile/nistath): the RFC 9380 hash-to-curve vectors arkworks tests its BLS12-381 G1 against.  Each of the
+      five gives Q0, Q1 (on the curve, outside the prime-order subgroup) and P = clear_cofactor(Q0 + Q1) =
+      h_eff * Q0 + h_eff * Q1 with h_eff = 0xd201000000010001 (RFC 9380 section 8.8.1; arkworks
+      bls12_381/src/curves/g1.rs clear_cofactor) -- a two-point MSM with a known answer, on points with full-size coordinates.
+      Written to bls12_381_hash_to_curve.json (checked below with the affine law on Python integers, independent of oracle/).
+
 These are DATA fixtures produced by the reference's own oracle (arkworks), not reference sources.
 Format: repeat { u64 LE n ; n x 48-byte compressed G1Affine } for points,
 repeat { u64 LE n ; n x 32-byte LE canonical scalar } for scalars, one 48-byte compressed point per
@@ -80,8 +88,45 @@ def import_bls12_381_points():
     return out
 
 
+H2C_TEST = ("/root/reference/open-division/prize4-msm-wasm/snarkify/zprize-prize4-15ac8c55-arkworks-algebra/ec/src/hashing/tests/"
+            "testdata/BLS12381G1_XMD-SHA-256_SSWU_RO_.json")
+H_EFF_381 = 0xd201000000010001
+R381 = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+
+
+def _affine_mul(k, P, p):
+    acc = None
+    while k:
+        if k & 1:
+            acc = _affine_add(acc, P, p)
+        P = _affine_add(P, P, p)
+        k >>= 1
+    return acc
+
+
+def import_bls12_381_hash_to_curve():
+    raw = open(H2C_TEST, "rb").read()
+    d = json.loads(raw)
+    assert d["curve"] == "BLS12-381 G1" and len(d["vectors"]) == 5
+    vectors = []
+    for v in d["vectors"]:
+        P, Q0, Q1 = [(int(v[k]["x"], 16), int(v[k]["y"], 16)) for k in ("P", "Q0", "Q1")]
+        assert all((y * y - x * x * x - 4) % P381 == 0 for x, y in (P, Q0, Q1))
+        assert _affine_mul(H_EFF_381, _affine_add(Q0, Q1, P381), P381) == P              # the known answer
+        assert _affine_mul(R381, P, P381) is None                                        # P is in G1 ...
+        assert _affine_mul(R381, Q0, P381) is not None and _affine_mul(R381, Q1, P381) is not None   # ... Q0, Q1 are not
+        vectors.append({"msg": v["msg"], "P": ["%096x" % c for c in P], "Q0": ["%096x" % c for c in Q0], "Q1": ["%096x" % c for c in Q1]})
+    out = {"source": H2C_TEST.replace("/root/reference/", ""), "source_sha256": hashlib.sha256(raw).hexdigest(),
+           "form": "canonical affine (x, y), big-endian hex, not Montgomery",
+           "relation": "P = h_eff * Q0 + h_eff * Q1 (clear_cofactor of Q0 + Q1)", "h_eff": "%x" % H_EFF_381, "vectors": vectors}
+    with open(os.path.join(HERE, "bls12_381_hash_to_curve.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    return out
+
+
 def main():
     import_bls12_381_points()
+    import_bls12_381_hash_to_curve()
     manifest = {}
     for dst, src in FILES.items():
         out = os.path.join(HERE, dst)

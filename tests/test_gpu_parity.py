@@ -561,6 +561,23 @@ def test_bls12_381_reference_points_through_the_engine(M, oracle, bls381_small_m
     assert np.array_equal(got, O.jac_to_affine(O.ark_msm(pts, sc, 1), 1)[0])
 
 
+@pytest.mark.skipif(os.environ.get("B200MSM_RUN_UNVERIFIED_TESTS") != "1",
+                    reason="written after the round's GPU minutes were spent: never run on a GPU yet (B200MSM_RUN_UNVERIFIED_TESTS=1 runs it)")
+def test_bls12_381_hash_to_curve_vectors_through_the_engine(M, oracle, bls381_hash_to_curve):
+    """The BLS12-381 MSM known answers of tests/test_oracle_golden.py::test_bls12_381_hash_to_curve_vectors_as_two_point_msms
+    (arkworks' RFC 9380 vectors: P = h_eff * Q0 + h_eff * Q1, Q0 and Q1 on the curve but outside G1) through the engine."""
+    O = oracle
+    vectors, h = bls381_hash_to_curve
+    sc = np.zeros((2, 32), np.uint8)
+    sc[:] = np.frombuffer(h.to_bytes(32, "little"), np.uint8)
+    for bases, want in vectors:
+        eng = M.Engine(M.BLS12_381)
+        eng.set_bases(bases)
+        got = _engine_result(M, O, eng, sc, 1)
+        eng.close()
+        assert np.array_equal(got, want)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Round 2: BASELINE configs 3 and 5 at their full sizes, the folded-window plans at scale, bases outside G1
 def _closed_form_check(M, O, curve, n, window_bits=0, tables=0, chunk_rows=1 << 24, expect_plan=None):

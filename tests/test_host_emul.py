@@ -281,6 +281,26 @@ def test_curve_ops(emul, oracle, curve):
     assert np.array_equal(O.xyzz_to_affine(da, curve), O.jac_to_affine(O.jac_double(_jac_from_aff(O, A, curve), curve), curve))
 
 
+def test_curve_ops_reproduce_rfc9380_cofactor_clearing(emul, oracle, bls381_hash_to_curve):
+    """The XYZZ arithmetic of csrc/ec.cuh (host build) on the reference's own BLS12-381 known answers: arkworks' RFC 9380
+    hash-to-curve vectors give Q0, Q1 (on the curve, outside G1, full-size coordinates) and P = h_eff * Q0 + h_eff * Q1.
+    h_eff * Q by double-and-add with dbl / madd, the two halves joined with the full XYZZ add."""
+    O = oracle
+    vectors, h = bls381_hash_to_curve
+    Q = np.concatenate([b for b, _ in vectors])                      # Q0, Q1 of vector 0, of vector 1, ...
+    n = len(Q)
+    q96 = np.ascontiguousarray(Q[:, :96])
+    acc = _xyzz_from_aff(O, Q, 1)                                    # top bit of h_eff
+    for bit in bin(h)[3:]:
+        emul.emul_ec_op(1, 2, _p(acc), None, n, 1)
+        if bit == "1":
+            emul.emul_ec_op(1, 0, _p(acc), _p(q96), n, 1)
+    lhs, rhs = np.ascontiguousarray(acc[0::2]), np.ascontiguousarray(acc[1::2])
+    emul.emul_ec_op(1, 1, _p(lhs), _p(rhs), n // 2, 1)
+    want = np.stack([w for _, w in vectors])
+    assert np.array_equal(O.xyzz_to_affine(lhs, 1), want)
+
+
 def test_te_constants(emul):
     """Twisted-Edwards parameters of BLS12-377 G1 re-derived from p: s = 1/sqrt 3, A = -3s, B = s, a1 = (A+2)/B,
     d1 = (A-2)/B, f = sqrt(-a1), d = -d1/a1 (= arkworks' COEFF_D, P1B/nickray/driver/bls12-377/src/curves/g1.rs:93)."""

@@ -146,3 +146,35 @@ def test_bls12_381_small_multiples_of_the_generator(oracle, bls381_small_multipl
     exp = KA.expected_affine(oracle, 1, t)
     assert np.array_equal(oracle.jac_to_affine(oracle.ark_msm(aff, sc, 1), 1)[0], exp)
     assert np.array_equal(oracle.jac_to_affine(oracle.naive_msm(aff, sc, 1), 1)[0], exp)
+
+
+def test_bls12_381_hash_to_curve_vectors_as_two_point_msms(oracle, bls381_hash_to_curve):
+    """A BLS12-381 G1 MSM known answer from the reference's own test data: arkworks' RFC 9380 hash-to-curve vectors
+    (.../arkworks-algebra/ec/src/hashing/tests/testdata/BLS12381G1_XMD-SHA-256_SSWU_RO_.json, five of them) give Q0, Q1 and
+    P = clear_cofactor(Q0 + Q1) = h_eff * Q0 + h_eff * Q1 -- points with full-size coordinates, Q0 and Q1 on the curve but
+    OUTSIDE the prime-order subgroup (arkworks' MSM is correct for every on-curve point, short_weierstrass_jacobian.rs:662-729).
+    The C restatement of arkworks' Pippenger, the naive sum and the Python big-integer oracle must all return P."""
+    vectors, h = bls381_hash_to_curve
+    c = oracle.constants(1)
+    sc = np.zeros((2, 32), np.uint8)
+    sc[:] = np.frombuffer(h.to_bytes(32, "little"), np.uint8)
+    total = None
+    for bases, want in vectors:
+        assert oracle.on_curve(bases, 1) and oracle.on_curve(want[None], 1)
+        assert np.array_equal(oracle.jac_to_affine(oracle.ark_msm(bases, sc, 1), 1)[0], want)
+        assert np.array_equal(oracle.jac_to_affine(oracle.naive_msm(bases, sc, 1), 1)[0], want)
+        q = [RB.from_mont_affine_bytes(b.tobytes(), 1) for b in bases]
+        got = RB.add(RB.mul(h, q[0], c["p"]), RB.mul(h, q[1], c["p"]), c["p"])
+        assert RB.to_mont_affine_bytes(got, 1) == want.tobytes()
+        assert RB.mul(c["r"], got, c["p"]) is None and RB.mul(c["r"], q[0], c["p"]) is not None     # P in G1, Q0 not
+        total = RB.add(total, got, c["p"])
+    # all ten bases in one MSM, distinct scalars h_eff * k_i (64 + 8 bits): sum k_i (P-part) via the big-integer law
+    bases = np.concatenate([b for b, _ in vectors])
+    ks = list(range(3, 13))
+    sc10 = np.stack([np.frombuffer((h * k).to_bytes(32, "little"), np.uint8) for k in ks])
+    want = None
+    for (b, _), i in zip(vectors, range(5)):
+        for j in range(2):
+            want = RB.add(want, RB.mul(h * ks[2 * i + j], RB.from_mont_affine_bytes(b[j].tobytes(), 1), c["p"]), c["p"])
+    assert oracle.jac_to_affine(oracle.ark_msm(bases, sc10, 1), 1)[0].tobytes() == RB.to_mont_affine_bytes(want, 1)
+
