@@ -25,8 +25,10 @@
  *
  * Parity pin: the five arkworks-generated known-answer instances in tests/golden/ark377_*.bin
  * (copied by tests/golden/make_golden.py) are reproduced byte-exactly by this file
- * (tests/test_oracle_golden.py).  BLS12-381 has no vector in the reference: for that curve parity is
- * "unpinned" by reference data and rests on oracle/ref_bigint.py (independent big-int) agreement.
+ * (tests/test_oracle_golden.py).  BLS12-381 has no file of MSM vectors in the reference; it is pinned on what the
+ * reference's test data does hold: arkworks' five RFC 9380 hash-to-curve vectors read as two-point MSMs
+ * (P = h_eff Q0 + h_eff Q1, tests/golden/bls12_381_hash_to_curve.json) and ten k G points of the wasm entry's tests,
+ * all reproduced by this file, and beyond that on agreement with oracle/ref_bigint.py (independent big-int).
  *
  * Build: make -C oracle   ->  oracle/liboracle.so   (gcc -O3 -pthread; no -march=native: the .so travels to the GPU box)
  */
